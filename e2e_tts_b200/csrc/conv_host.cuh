@@ -1,0 +1,198 @@
+// Host side of the tcgen05 convolution: TMA tensor-map creation (driver entry point fetched at run time,
+// so the library does not link libcuda), launch-plan sizing and the weight packer that writes the swizzled
+// shared-memory images the kernel streams with 1-D bulk copies.
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "conv_tc.cuh"
+
+namespace e2e {
+
+inline std::string& last_error() {
+  static thread_local std::string s;
+  return s;
+}
+inline int fail(int code, const std::string& msg) {
+  last_error() = msg;
+  return code;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// Tensor map over a channels-last bf16 activation tensor [B][T][C]: dims (C, T, B), box (ch_box, box_rows, 1).
+// ch_box = 64 -> SWIZZLE_128B, ch_box = 32 -> SWIZZLE_64B.  Out-of-bounds -> zeros.
+inline int make_act_tensor_map(CUtensorMap* tm, const void* base, int B, int T, int C, int ch_box, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(-10, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)T * C * 2};
+  cuuint32_t box[3] = {(cuuint32_t)ch_box, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMapSwizzle sw = ch_box == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) B=%d T=%d C=%d box=%dx%d", (int)r, B, T, C, ch_box,
+             box_rows);
+    return fail(-11, buf);
+  }
+  return 0;
+}
+
+// Static description of one convolution layer as the GEMM the kernel runs.
+struct ConvShape {
+  int cin;       // padded input channels (32, or a multiple of 64)
+  int n_total;   // output columns (C_out, or u*C_out for polyphase ConvTranspose)
+  int nt;        // columns per CTA
+  int taps;      // taps per N tile
+  std::vector<int> shifts;  // [n_tiles][taps] row shifts
+};
+
+constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
+
+struct ConvPlan {
+  ConvParams p{};
+  CUtensorMap tm{};
+  dim3 grid{};
+  int smem_bytes = 0;
+};
+
+// Fill every geometry field of plan.p from the layer shape and the problem size.  `mt_pref` = preferred
+// number of 128-row tiles per CTA (reduced until TMEM and shared memory fit).
+inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pref) {
+  ConvParams& p = plan.p;
+  if (s.cin != 32 && s.cin % 64 != 0) return fail(-2, "cin must be 32 or a multiple of 64");
+  if (s.nt % 32 != 0 || s.nt > 256 || s.n_total % s.nt != 0) return fail(-2, "bad N tiling");
+  const int n_tiles = s.n_total / s.nt;
+  if (n_tiles > kMaxNTiles || s.taps > kMaxTaps) return fail(-2, "too many N tiles / taps");
+  p.T = T;
+  p.B = B;
+  p.rowb = s.cin == 32 ? 64 : 128;
+  p.panels = s.cin == 32 ? 1 : s.cin / 64;
+  if (p.panels > kMaxPanels) return fail(-2, "too many K panels");
+  p.nt = s.nt;
+  p.n_total = s.n_total;
+  p.taps = s.taps;
+  int smin = 0, smax = 0;
+  for (int i = 0; i < n_tiles; ++i)
+    for (int j = 0; j < s.taps; ++j) {
+      const int sh = s.shifts[i * s.taps + j];
+      if (sh < -127 || sh > 127) return fail(-2, "tap shift out of range");
+      p.shift[i][j] = (int8_t)sh;
+      smin = sh < smin ? sh : smin;
+      smax = sh > smax ? sh : smax;
+    }
+  p.hl = -smin;
+  const int tile_bytes = s.nt * p.rowb;
+  const int total_tiles = p.panels * s.taps;
+  // ring stage ~ 32 KB (or the whole weight set when it is smaller)
+  int tpc = 32768 / tile_bytes;
+  if (tpc < 1) tpc = 1;
+  if (tpc > total_tiles) tpc = total_tiles;
+  p.tiles_per_chunk = tpc;
+  p.n_chunks = (total_tiles + tpc - 1) / tpc;
+  p.stage_bytes = tpc * tile_bytes;
+  const int bar_bytes = 256;
+  for (int mt = mt_pref; mt >= 1; mt >>= 1) {
+    if (mt * s.nt > 512) continue;
+    const int need = 128 * mt + p.hl + smax;
+    for (int box = 128; box >= 16; box >>= 1) {
+      const int rows = (need + box - 1) / box * box;
+      if (rows - need > 32 && box > 16) continue;  // avoid large padding
+      const int slab = p.panels * rows * p.rowb;
+      int stages = (kSmemLimit - 1024 - bar_bytes - slab) / p.stage_bytes;
+      if (stages > p.n_chunks) stages = p.n_chunks;
+      if (stages > 4) stages = 4;
+      if (stages < (p.n_chunks > 1 ? 2 : 1)) continue;
+      p.mt = mt;
+      p.slab_rows = rows;
+      p.box_rows = box;
+      p.n_stages = stages;
+      int cols = 32;
+      while (cols < mt * s.nt) cols <<= 1;
+      p.tmem_cols = cols;
+      plan.smem_bytes = 1024 + slab + stages * p.stage_bytes + bar_bytes;
+      plan.grid = dim3((T + 128 * mt - 1) / (128 * mt), n_tiles, B);
+      return 0;
+    }
+  }
+  return fail(-3, "convolution does not fit shared memory / TMEM");
+}
+
+inline int launch_conv(const ConvPlan& plan, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e != cudaSuccess) return fail((int)e, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    attr_set = true;
+  }
+  conv_tc_kernel<<<plan.grid, kConvThreads, plan.smem_bytes, st>>>(plan.tm, plan.p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, std::string("conv_tc launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Weight packing.  `wt(n, ci, tap_index_within_tile, n_tile)` semantics are supplied by the caller through a
+// dense fp32 array  wg[n_total][taps][cin]  (already folded, already arranged per GEMM column): the packer
+// only casts to bf16 and lays the bytes out as swizzled smem tiles [n_tile][panel][tap][nt][rowb].
+// ---------------------------------------------------------------------------------------------------
+inline uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf16_to_f32(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+inline size_t packed_weight_bytes(const ConvShape& s) {
+  return (size_t)s.n_total * s.taps * s.cin * 2;
+}
+
+inline void pack_conv_weights(const ConvShape& s, const float* wg, uint8_t* out) {
+  const int rowb = s.cin == 32 ? 64 : 128;
+  const int panels = s.cin == 32 ? 1 : s.cin / 64;
+  const int chp = rowb / 2;
+  const uint32_t mask = rowb == 128 ? 7u : 3u;
+  const int n_tiles = s.n_total / s.nt;
+  const size_t tile_bytes = (size_t)s.nt * rowb;
+  for (int nti = 0; nti < n_tiles; ++nti)
+    for (int pn = 0; pn < panels; ++pn)
+      for (int tap = 0; tap < s.taps; ++tap) {
+        uint8_t* tile = out + (((size_t)nti * panels + pn) * s.taps + tap) * tile_bytes;
+        for (int r = 0; r < s.nt; ++r) {
+          const float* src = wg + ((size_t)(nti * s.nt + r) * s.taps + tap) * s.cin + pn * chp;
+          for (int c = 0; c < chp; ++c) {
+            const uint32_t off = swizzle_off((uint32_t)(r * rowb + c * 2), mask);
+            const uint16_t h = f32_to_bf16_rn(src[c]);
+            memcpy(tile + off, &h, 2);
+          }
+        }
+      }
+}
+
+}  // namespace e2e
