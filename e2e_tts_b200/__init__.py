@@ -1,0 +1,11 @@
+"""e2e_tts_b200 — B200-native (sm_100a) implementation of the e2e-tts synthesis hot path.
+
+Drop-in names (same signatures as the reference, see each module's docstring):
+    HifiGan, ResBlock1, ResBlock2, get_padding, init_weights   <- e2e_tts/models/vocoder/{generator,layers,function}.py
+    TorchSTFT, generate_melspecs, dynamic_range_compression     <- e2e_tts/src/tools/{stft,utils}.py
+"""
+from .vocoder import HifiGan, ResBlock1, ResBlock2, get_padding, init_weights, LRELU_SLOPE  # noqa: F401
+from .stft import TorchSTFT, generate_melspecs, dynamic_range_compression, dynamic_range_decompression  # noqa: F401
+
+__all__ = ["HifiGan", "ResBlock1", "ResBlock2", "get_padding", "init_weights", "TorchSTFT", "generate_melspecs",
+           "dynamic_range_compression", "dynamic_range_decompression"]

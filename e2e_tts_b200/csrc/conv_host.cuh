@@ -7,17 +7,9 @@
 #include <string>
 #include <vector>
 #include "conv_tc.cuh"
+#include "errors.h"
 
 namespace e2e {
-
-inline std::string& last_error() {
-  static thread_local std::string s;
-  return s;
-}
-inline int fail(int code, const std::string& msg) {
-  last_error() = msg;
-  return code;
-}
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

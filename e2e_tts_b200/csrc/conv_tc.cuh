@@ -41,8 +41,7 @@ struct ConvParams {
   int n_stages;         // ring depth
   int stage_bytes;      // bytes per ring stage (multiple of 1024)
   int tmem_cols;        // power of two >= max(32, mt*nt)
-  int base_off_mode;    // experiment switch: 1 = put (addr>>7)&7 in the descriptor's base-offset field
-  int div3;             // epilogue: divide by 3 (reference generator.py:48, xs / num_kernels)
+  float divisor;        // epilogue: 0 = none, else out /= divisor (generator.py:48, xs / num_kernels)
   float slope;          // LeakyReLU slope applied to out_act
   int8_t shift[kMaxNTiles][kMaxTaps];  // row shift of each tap, per N tile
   const uint8_t* w;     // packed weights
@@ -148,8 +147,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
           for (int m = 0; m < p.mt; ++m) {
             for (int ks = 0; ks < ksteps; ++ks) {
               const uint32_t a_addr = a_base + m * 128 * rowb + ks * 32;
-              const uint32_t boff = p.base_off_mode ? ((a_addr >> 7) & 7u) : 0u;
-              const uint64_t da = umma_smem_desc(a_addr, rowb, boff);
+              const uint64_t da = umma_smem_desc(a_addr, rowb, 0);
               const uint64_t db = umma_smem_desc(b_base + ks * 32, rowb, 0);
               umma_bf16(tmem_base + m * p.nt, da, db, idesc, (tile | ks) != 0 ? 1u : 0u);
             }
@@ -199,9 +197,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
               f[i] += r.x; f[i + 1] += r.y; f[i + 2] += r.z; f[i + 3] += r.w;
             }
           }
-          if (p.div3) {
+          if (p.divisor != 0.f) {
+            const float dv = p.divisor;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = f[i] / 3.0f;
+            for (int i = 0; i < 32; ++i) f[i] = f[i] / dv;
           }
           if (p.out_f32) {
 #pragma unroll

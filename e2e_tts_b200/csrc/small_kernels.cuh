@@ -1,0 +1,69 @@
+// CUDA-core kernels at the two ends of the generator, where the work is a layout change or a dot product
+// rather than a GEMM:
+//   * mel_to_act:    [B,80,T] fp32 (any strides; the reference passes a transposed view, utils.py:144)
+//                    -> channels-last bf16 [B][T][cin_pad] operand of conv_pre (padding channels = 0)
+//   * post_conv_tanh: conv_post (Conv1d C->1, k=7, pad 3) + tanh  (generator.py:50-51).  Its input is the
+//                    previous epilogue's leaky_relu(x, 0.01) in bf16 (generator.py:49), N = 1 so this is a
+//                    224-term dot product per sample, bandwidth-shaped.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace e2e {
+
+__global__ void mel_to_act_kernel(const float* __restrict__ mel, long long sB, long long sC, long long sT, int B,
+                                  int T, int C, int cpad, __nv_bfloat16* __restrict__ out) {
+  const int G = cpad / 8;
+  const long long total = (long long)B * T * G;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int t = (int)(idx % T);
+  const int g = (int)((idx / T) % G);
+  const int b = (int)(idx / ((long long)T * G));
+  uint32_t pk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c0 = g * 8 + 2 * i;
+    const float a = c0 < C ? mel[b * sB + c0 * sC + t * sT] : 0.f;
+    const float c = c0 + 1 < C ? mel[b * sB + (c0 + 1) * sC + t * sT] : 0.f;
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
+    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(out + ((long long)b * T + t) * cpad + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+
+constexpr int kPostMaxW = 7 * 64;
+
+// w: [k][C] fp32 (tap-major), one output channel.
+__global__ void __launch_bounds__(256)
+post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, float bias, int B, int T,
+                      int C, int k, float* __restrict__ wav) {
+  __shared__ float sw[kPostMaxW];
+  for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= T) return;
+  const int half = (k - 1) / 2;
+  float acc = bias;
+  for (int j = 0; j < k; ++j) {
+    const int tt = t + j - half;
+    if (tt < 0 || tt >= T) continue;
+    const uint4* row = reinterpret_cast<const uint4*>(act + ((long long)b * T + tt) * C);
+    const float* wj = sw + j * C;
+    for (int c8 = 0; c8 < C / 8; ++c8) {
+      const uint4 v = row[c8];
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
+        acc = fmaf(__low2float(h), wj[c8 * 8 + 2 * i], acc);
+        acc = fmaf(__high2float(h), wj[c8 * 8 + 2 * i + 1], acc);
+      }
+    }
+  }
+  wav[(long long)b * T + t] = tanhf(acc);
+}
+
+}  // namespace e2e

@@ -1,0 +1,468 @@
+// HiFi-GAN generator on B200: layer table, weight packing, launch plans and the forward pass.
+// Mirrors the structure of the reference generator (e2e_tts/models/vocoder/generator.py:13-53 and
+// layers.py:10-69) as a list of tcgen05 convolution launches plus two small CUDA-core kernels.
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+#include "../../include/e2e_tts_b200.h"
+#include "conv_host.cuh"
+#include "small_kernels.cuh"
+
+using namespace e2e;
+
+namespace {
+
+enum LayerKind { L_CONV = 0, L_CONVT = 1, L_POST = 2 };
+
+struct Layer {
+  std::string name;
+  LayerKind kind;
+  int cin, cout, k, dil, u;  // reference shapes (u = stride of ConvTranspose1d)
+  ConvShape shape;           // GEMM form (L_CONV / L_CONVT)
+  uint8_t* d_w = nullptr;    // packed bf16 weights (or fp32 [k][cin] for L_POST)
+  float* d_bias = nullptr;   // [n_total]
+  float post_bias = 0.f;
+  bool loaded = false;
+};
+
+struct Op {
+  int kind;   // 0 = mel_to_act, 1 = conv_tc, 2 = post
+  int layer;  // index into layers
+  ConvPlan plan;
+};
+
+struct PlanKey {
+  int B, T;
+  const void* ws;
+  const void* wav;
+  bool operator<(const PlanKey& o) const {
+    if (B != o.B) return B < o.B;
+    if (T != o.T) return T < o.T;
+    if (ws != o.ws) return ws < o.ws;
+    return wav < o.wav;
+  }
+};
+
+struct Buffers {
+  __nv_bfloat16 *melA, *preA, *A0, *A1, *M, *Y;
+  float *X0, *X1, *SUM;
+  size_t total;
+};
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+struct e2e_voc {
+  e2e_voc_config cfg;
+  std::vector<Layer> layers;
+  std::map<std::string, int> by_name;
+  std::map<PlanKey, std::vector<Op>> plans;
+  int cin_pad = 0;
+  int hop = 1;
+  int n_sms = 148;
+};
+
+static int pick_nt(int cout) { return cout >= 256 ? 256 : cout; }
+
+static void add_conv(e2e_voc* v, const std::string& name, int cin, int cin_pad, int cout, int k, int dil) {
+  Layer L;
+  L.name = name;
+  L.kind = L_CONV;
+  L.cin = cin;
+  L.cout = cout;
+  L.k = k;
+  L.dil = dil;
+  L.u = 1;
+  L.shape.cin = cin_pad;
+  L.shape.n_total = cout;
+  L.shape.nt = pick_nt(cout);
+  L.shape.taps = k;
+  const int n_tiles = cout / L.shape.nt;
+  for (int i = 0; i < n_tiles; ++i)
+    for (int j = 0; j < k; ++j) L.shape.shifts.push_back((j - (k - 1) / 2) * dil);
+  v->by_name[name] = (int)v->layers.size();
+  v->layers.push_back(L);
+}
+
+// ConvTranspose1d(cin, cout, k = 2u, stride = u, padding = u/2) in polyphase form (SURVEY.md §8 a'5):
+// output sample n = q*u + p, j0 = p + u/2:  y = W[:, :, j0]^T x[q] + (j0 < u ? W[:, :, j0+u]^T x[q-1]
+//                                                                        : W[:, :, j0-u]^T x[q+1]).
+// GEMM column n' = p*cout + co, so row q of the GEMM output IS the u output samples in channels-last order.
+static int add_convt(e2e_voc* v, const std::string& name, int cin, int cout, int k, int u) {
+  if (k != 2 * u || (u & 1)) return fail(-4, "ConvTranspose1d supported for kernel == 2*stride, even stride");
+  Layer L;
+  L.name = name;
+  L.kind = L_CONVT;
+  L.cin = cin;
+  L.cout = cout;
+  L.k = k;
+  L.dil = 1;
+  L.u = u;
+  L.shape.cin = cin;
+  L.shape.n_total = u * cout;
+  int nt = cout;  // one phase per tile, widened while the tile stays inside one half of the phases
+  while (nt * 2 <= 256 && ((u / 2) % (nt * 2 / cout)) == 0) nt *= 2;
+  if (nt > 256) return fail(-4, "ConvTranspose1d output channels > 256 unsupported");
+  L.shape.nt = nt;
+  L.shape.taps = 2;
+  const int n_tiles = L.shape.n_total / nt;
+  for (int i = 0; i < n_tiles; ++i) {
+    const int p = (i * nt) / cout;
+    L.shape.shifts.push_back(0);
+    L.shape.shifts.push_back(p < u / 2 ? -1 : +1);
+  }
+  v->by_name[name] = (int)v->layers.size();
+  v->layers.push_back(L);
+  return 0;
+}
+
+extern "C" int e2e_voc_create(const e2e_voc_config* cfg, e2e_voc** out) {
+  if (!cfg || !out) return fail(-1, "null argument");
+  if (cfg->num_upsamples < 1 || cfg->num_upsamples > E2E_MAX_UPSAMPLES || cfg->num_kernels < 1 ||
+      cfg->num_kernels > E2E_MAX_KERNELS)
+    return fail(-1, "bad num_upsamples / num_kernels");
+  std::unique_ptr<e2e_voc> v(new e2e_voc);
+  v->cfg = *cfg;
+  const int C0 = cfg->upsample_initial_channel;
+  if (C0 % 64 != 0 || C0 > 512) return fail(-4, "upsample_initial_channel must be a multiple of 64, <= 512");
+  if (cfg->in_channels < 1 || cfg->in_channels > 512) return fail(-4, "in_channels out of range");
+  v->cin_pad = (cfg->in_channels + 63) / 64 * 64;
+  add_conv(v.get(), "conv_pre", cfg->in_channels, v->cin_pad, C0, 7, 1);
+  int ch = C0;
+  v->hop = 1;
+  for (int i = 0; i < cfg->num_upsamples; ++i) {
+    const int cout = ch / 2;
+    if (cout != 32 && cout % 64 != 0) return fail(-4, "stage channel count must be 32 or a multiple of 64");
+    int rc = add_convt(v.get(), "ups." + std::to_string(i), ch, cout, cfg->upsample_kernel_sizes[i],
+                       cfg->upsample_rates[i]);
+    if (rc) return rc;
+    v->hop *= cfg->upsample_rates[i];
+    ch = cout;
+  }
+  ch = C0;
+  for (int i = 0; i < cfg->num_upsamples; ++i) {
+    ch /= 2;
+    for (int j = 0; j < cfg->num_kernels; ++j) {
+      const int k = cfg->resblock_kernel_sizes[j];
+      if (!(k & 1) || k > kMaxTaps) return fail(-4, "resblock kernel size must be odd and <= 15");
+      const int nd = cfg->num_dilations[j];
+      if (nd < 1 || nd > E2E_MAX_DILATIONS) return fail(-1, "bad num_dilations");
+      const std::string base = "resblocks." + std::to_string(i * cfg->num_kernels + j);
+      for (int m = 0; m < nd; ++m) {
+        const int d = cfg->resblock_dilation_sizes[j][m];
+        if ((k - 1) / 2 * d > 127) return fail(-4, "dilated receptive field too wide");
+        if (cfg->resblock == 1) {
+          add_conv(v.get(), base + ".convs1." + std::to_string(m), ch, ch, ch, k, d);
+          add_conv(v.get(), base + ".convs2." + std::to_string(m), ch, ch, ch, k, 1);
+        } else {
+          add_conv(v.get(), base + ".convs." + std::to_string(m), ch, ch, ch, k, d);
+        }
+      }
+    }
+  }
+  {
+    Layer L;
+    L.name = "conv_post";
+    L.kind = L_POST;
+    L.cin = ch;
+    L.cout = 1;
+    L.k = 7;
+    L.dil = 1;
+    L.u = 1;
+    if (ch * 7 > kPostMaxW || ch % 8) return fail(-4, "conv_post input channels unsupported");
+    v->by_name[L.name] = (int)v->layers.size();
+    v->layers.push_back(L);
+  }
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail((int)e, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
+  cudaDeviceGetAttribute(&v->n_sms, cudaDevAttrMultiProcessorCount, dev);
+  *out = v.release();
+  return 0;
+}
+
+extern "C" void e2e_voc_destroy(e2e_voc* v) {
+  if (!v) return;
+  for (auto& L : v->layers) {
+    if (L.d_w) cudaFree(L.d_w);
+    if (L.d_bias) cudaFree(L.d_bias);
+  }
+  delete v;
+}
+
+extern "C" int e2e_voc_hop(const e2e_voc* v) { return v ? v->hop : 0; }
+
+extern "C" int e2e_voc_missing_layers(const e2e_voc* v) {
+  if (!v) return -1;
+  int n = 0;
+  for (auto& L : v->layers) n += L.loaded ? 0 : 1;
+  return n;
+}
+
+extern "C" int e2e_voc_load_layer(e2e_voc* v, const char* name, const float* weight, int64_t weight_numel,
+                                  const float* bias, int64_t bias_numel) {
+  if (!v || !name || !weight || !bias) return fail(-1, "null argument");
+  auto it = v->by_name.find(name);
+  if (it == v->by_name.end()) return fail(-5, std::string("unknown layer: ") + name);
+  Layer& L = v->layers[it->second];
+  const int64_t want_w = (int64_t)L.cin * L.cout * L.k;
+  if (weight_numel != want_w || bias_numel != L.cout)
+    return fail(-6, std::string("shape mismatch for layer ") + name);
+  cudaError_t e;
+  if (L.kind == L_POST) {
+    // reference layout [1][cin][k] -> [k][cin]
+    std::vector<float> w((size_t)L.k * L.cin);
+    for (int c = 0; c < L.cin; ++c)
+      for (int j = 0; j < L.k; ++j) w[(size_t)j * L.cin + c] = weight[(size_t)c * L.k + j];
+    if (!L.d_w && (e = cudaMalloc(&L.d_w, w.size() * 4)) != cudaSuccess) return fail((int)e, "cudaMalloc");
+    if ((e = cudaMemcpy(L.d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+      return fail((int)e, "cudaMemcpy");
+    L.post_bias = bias[0];
+    L.loaded = true;
+    v->plans.clear();
+    return 0;
+  }
+  const ConvShape& s = L.shape;
+  std::vector<float> wg((size_t)s.n_total * s.taps * s.cin, 0.f);
+  std::vector<float> bg(s.n_total);
+  if (L.kind == L_CONV) {
+    // [cout][cin][k] -> wg[co][tap][ci]
+    for (int co = 0; co < L.cout; ++co) {
+      for (int ci = 0; ci < L.cin; ++ci)
+        for (int j = 0; j < L.k; ++j)
+          wg[((size_t)co * s.taps + j) * s.cin + ci] = weight[((size_t)co * L.cin + ci) * L.k + j];
+      bg[co] = bias[co];
+    }
+  } else {
+    // [cin][cout][2u] -> column n = p*cout + co, tap 0 = W[..., j0], tap 1 = W[..., j0 +/- u]
+    const int u = L.u;
+    for (int p = 0; p < u; ++p) {
+      const int j0 = p + u / 2;
+      const int j1 = j0 < u ? j0 + u : j0 - u;
+      for (int co = 0; co < L.cout; ++co) {
+        const int n = p * L.cout + co;
+        for (int ci = 0; ci < L.cin; ++ci) {
+          const float* wsrc = weight + ((size_t)ci * L.cout + co) * L.k;
+          wg[((size_t)n * 2 + 0) * s.cin + ci] = wsrc[j0];
+          wg[((size_t)n * 2 + 1) * s.cin + ci] = wsrc[j1];
+        }
+        bg[n] = bias[co];
+      }
+    }
+  }
+  std::vector<uint8_t> packed(packed_weight_bytes(s));
+  pack_conv_weights(s, wg.data(), packed.data());
+  if (!L.d_w && (e = cudaMalloc(&L.d_w, packed.size())) != cudaSuccess) return fail((int)e, "cudaMalloc");
+  if (!L.d_bias && (e = cudaMalloc(&L.d_bias, bg.size() * 4)) != cudaSuccess) return fail((int)e, "cudaMalloc");
+  if ((e = cudaMemcpy(L.d_w, packed.data(), packed.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return fail((int)e, "cudaMemcpy");
+  if ((e = cudaMemcpy(L.d_bias, bg.data(), bg.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+    return fail((int)e, "cudaMemcpy");
+  L.loaded = true;
+  v->plans.clear();
+  return 0;
+}
+
+static size_t stage_elems(const e2e_voc* v, int B, int T) {
+  // largest rows*channels product over the resblock stages
+  size_t best = 0;
+  int ch = v->cfg.upsample_initial_channel, rate = 1;
+  for (int i = 0; i < v->cfg.num_upsamples; ++i) {
+    ch /= 2;
+    rate *= v->cfg.upsample_rates[i];
+    const size_t e = (size_t)B * T * rate * ch;
+    best = e > best ? e : best;
+  }
+  return best;
+}
+
+static void carve(const e2e_voc* v, int B, int T, void* ws, Buffers& b) {
+  uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* r = p ? p + off : nullptr;
+    off += align_up(bytes, 1024);
+    return r;
+  };
+  const size_t E = stage_elems(v, B, T);
+  b.melA = (__nv_bfloat16*)take((size_t)B * T * v->cin_pad * 2);
+  b.preA = (__nv_bfloat16*)take((size_t)B * T * v->cfg.upsample_initial_channel * 2);
+  b.A0 = (__nv_bfloat16*)take(E * 2);
+  b.A1 = (__nv_bfloat16*)take(E * 2);
+  b.M = (__nv_bfloat16*)take(E * 2);
+  b.Y = (__nv_bfloat16*)take(E * 2);
+  b.X0 = (float*)take(E * 4);
+  b.X1 = (float*)take(E * 4);
+  b.SUM = (float*)take(E * 4);
+  b.total = off;
+}
+
+extern "C" size_t e2e_voc_workspace_bytes(const e2e_voc* v, int32_t B, int32_t T) {
+  if (!v || B < 1 || T < 1) return 0;
+  Buffers b;
+  carve(v, B, T, nullptr, b);
+  return b.total;
+}
+
+// One conv launch: input activation `in` ([B][T][cin] bf16), outputs as requested.
+static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int T, const __nv_bfloat16* in,
+                        const float* res_in, const float* sum_in, float* out_f32, __nv_bfloat16* out_act,
+                        float slope, float divisor) {
+  Layer& L = v->layers[layer];
+  Op op;
+  op.kind = 1;
+  op.layer = layer;
+  const ConvShape& s = L.shape;
+  int mt = 512 / s.nt;
+  if (mt > 4) mt = 4;
+  const int n_tiles = s.n_total / s.nt;
+  // keep at least ~2 waves of CTAs when the problem allows it
+  while (mt > 1 && (long long)((T + 128 * mt - 1) / (128 * mt)) * n_tiles * B < 2LL * v->n_sms) mt >>= 1;
+  int rc = plan_conv(op.plan, s, B, T, mt);
+  if (rc) return rc;
+  ConvParams& p = op.plan.p;
+  rc = make_act_tensor_map(&op.plan.tm, in, B, T, s.cin, p.rowb / 2, p.box_rows);
+  if (rc) return rc;
+  p.w = L.d_w;
+  p.bias = L.d_bias;
+  p.res_in = res_in;
+  p.sum_in = sum_in;
+  p.out_f32 = out_f32;
+  p.out_act = out_act;
+  p.slope = slope;
+  p.divisor = divisor;
+  ops.push_back(op);
+  return 0;
+}
+
+static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) {
+  Buffers bf;
+  carve(v, B, T, ws, bf);
+  const e2e_voc_config& c = v->cfg;
+  const float kSlope = 0.1f;  // LRELU_SLOPE, generator.py:10 / layers.py:7
+  {
+    Op op;
+    op.kind = 0;
+    op.layer = 0;
+    ops.push_back(op);
+  }
+  // conv_pre, then the first leaky_relu of the stage loop (generator.py:38-40)
+  int rc = make_conv_op(v, ops, v->by_name["conv_pre"], B, T, bf.melA, nullptr, nullptr, nullptr, bf.preA, kSlope, 0.f);
+  if (rc) return rc;
+  const __nv_bfloat16* stage_in = bf.preA;
+  int Ts = T;
+  for (int i = 0; i < c.num_upsamples; ++i) {
+    // x = ups[i](leaky_relu(x)) : writes the residual stream X0 (fp32) and its activation A0 (bf16)
+    rc = make_conv_op(v, ops, v->by_name["ups." + std::to_string(i)], B, Ts, stage_in, nullptr, nullptr, bf.X0,
+                      bf.A0, kSlope, 0.f);
+    if (rc) return rc;
+    Ts *= c.upsample_rates[i];
+    const bool last_stage = i + 1 == c.num_upsamples;
+    // F.leaky_relu(x) before conv_post uses the default slope 0.01 (generator.py:49)
+    const float out_slope = last_stage ? 0.01f : kSlope;
+    for (int j = 0; j < c.num_kernels; ++j) {
+      const std::string base = "resblocks." + std::to_string(i * c.num_kernels + j);
+      const int nd = c.num_dilations[j];
+      const float* xin = bf.X0;
+      const __nv_bfloat16* ain = bf.A0;
+      for (int m = 0; m < nd; ++m) {
+        const bool last = m + 1 == nd;
+        // where does x_new = conv(...) + x go?
+        float* of32 = bf.X1;
+        __nv_bfloat16* oact = bf.A1;
+        const float* sum_in = nullptr;
+        float divisor = 0.f, slope = kSlope;
+        if (last) {
+          oact = nullptr;
+          of32 = bf.SUM;
+          sum_in = j > 0 ? bf.SUM : nullptr;      // xs += resblock_j(x)   (generator.py:44-47)
+          if (j + 1 == c.num_kernels) {           // x = xs / num_kernels   (generator.py:48)
+            of32 = nullptr;
+            oact = bf.Y;
+            divisor = (float)c.num_kernels;
+            slope = out_slope;
+          }
+        }
+        if (c.resblock == 1) {
+          rc = make_conv_op(v, ops, v->by_name[base + ".convs1." + std::to_string(m)], B, Ts, ain, nullptr, nullptr,
+                            nullptr, bf.M, kSlope, 0.f);
+          if (rc) return rc;
+          rc = make_conv_op(v, ops, v->by_name[base + ".convs2." + std::to_string(m)], B, Ts, bf.M, xin, sum_in,
+                            of32, oact, slope, divisor);
+          if (rc) return rc;
+        } else {
+          rc = make_conv_op(v, ops, v->by_name[base + ".convs." + std::to_string(m)], B, Ts, ain, xin, sum_in, of32,
+                            oact, slope, divisor);
+          if (rc) return rc;
+        }
+        xin = bf.X1;
+        ain = bf.A1;
+      }
+    }
+    stage_in = bf.Y;
+  }
+  {
+    Op op;
+    op.kind = 2;
+    op.layer = v->by_name["conv_post"];
+    ops.push_back(op);
+  }
+  return 0;
+}
+
+extern "C" int e2e_voc_launches_per_forward(const e2e_voc* v) {
+  if (!v) return -1;
+  const e2e_voc_config& c = v->cfg;
+  int n = 3;  // mel_to_act, conv_pre, conv_post
+  for (int i = 0; i < c.num_upsamples; ++i) {
+    n += 1;
+    for (int j = 0; j < c.num_kernels; ++j) n += c.num_dilations[j] * (c.resblock == 1 ? 2 : 1);
+  }
+  return n;
+}
+
+extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B,
+                               int32_t T, float* wav, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!v || !mel || !wav || !workspace) return fail(-1, "null argument");
+  if (B < 1 || T < 1) return fail(-1, "B and T must be positive");
+  if (e2e_voc_missing_layers(v) != 0) return fail(-7, "e2e_voc_forward before all layers were loaded");
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(-1, "workspace must be 1024-byte aligned");
+  if (workspace_bytes < e2e_voc_workspace_bytes(v, B, T)) return fail(-1, "workspace too small");
+  if ((long long)T * v->hop > 0x7fffffffLL) return fail(-1, "utterance too long");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  PlanKey key{B, T, workspace, wav};
+  auto it = v->plans.find(key);
+  if (it == v->plans.end()) {
+    std::vector<Op> ops;
+    int rc = build_plan(v, B, T, workspace, ops);
+    if (rc) return rc;
+    if (v->plans.size() > 64) v->plans.clear();
+    it = v->plans.emplace(key, std::move(ops)).first;
+  }
+  Buffers bf;
+  carve(v, B, T, workspace, bf);
+  for (const Op& op : it->second) {
+    if (op.kind == 0) {
+      const long long total = (long long)B * T * (v->cin_pad / 8);
+      mel_to_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mel, sB, sC, sT, B, T, v->cfg.in_channels,
+                                                                        v->cin_pad, bf.melA);
+    } else if (op.kind == 1) {
+      int rc = launch_conv(op.plan, st);
+      if (rc) return rc;
+    } else {
+      const Layer& L = v->layers[op.layer];
+      const int Tout = T * v->hop;
+      dim3 grid((Tout + 255) / 256, B);
+      post_conv_tanh_kernel<<<grid, 256, 0, st>>>(bf.Y, reinterpret_cast<const float*>(L.d_w), L.post_bias, B, Tout,
+                                                  L.cin, L.k, wav);
+    }
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, std::string("e2e_voc_forward launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" const char* e2e_last_error_string(void) { return last_error().c_str(); }
+extern "C" const char* e2e_version_string(void) { return "e2e_tts_b200 0.1 sm_100a"; }

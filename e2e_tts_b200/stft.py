@@ -1,0 +1,191 @@
+"""Drop-in STFT -> log-mel front-end of e2e-tts on B200.
+
+Mirrors e2e_tts/src/tools/stft.py:11-89 (`TorchSTFT`), :107-135 (`generate_melspecs`) and
+e2e_tts/src/tools/utils.py:22-37 (`dynamic_range_compression/decompression`) as their callers use them
+(tools_for_data.py:108-115,178-179; dataloader.py:82-86,155,344-346,372-373; textgrid2durations.py:101-103,137):
+
+    stft = TorchSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0)
+    mel, energy = stft.mel_spectrogram(audio[B, L], return_energy=True)   # [B, 80, T], [B, T]
+
+One fused CUDA kernel does reflect padding, Hann windowing, the 1024-point real FFT, magnitude, the sparse mel
+filterbank, log-compression and the frame energy in a single pass over the audio.  CPU tensors are accepted, as
+in the reference call sites: they are staged to the current CUDA device and the results come back as CPU tensors
+(so the callers' `.numpy()` keeps working); CUDA tensors stay on the device.  There is no CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes
+import warnings
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _native
+
+
+def dynamic_range_compression(x, C=1, clip_val=1e-5):
+    """utils.py:22-28."""
+    return torch.log(torch.clamp(x, min=clip_val) * C)
+
+
+def dynamic_range_decompression(x, C=1):
+    """utils.py:31-37."""
+    return torch.exp(x) / C
+
+
+def slaney_mel_filterbank(sr: int, n_fft: int, n_mels: int, fmin: float, fmax: Optional[float]) -> np.ndarray:
+    """The filterbank the reference obtains from `librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax)`
+    (stft.py:34-40; librosa==0.9.2 defaults: Slaney mel scale, Slaney area normalisation, float32)."""
+    if fmax is None:
+        fmax = sr / 2.0
+    f_sp = 200.0 / 3.0
+    brk_hz, logstep = 1000.0, np.log(6.4) / 27.0
+    brk_mel = brk_hz / f_sp
+
+    def hz2mel(f):
+        return brk_mel + np.log(f / brk_hz) / logstep if f >= brk_hz else f / f_sp
+
+    def mel2hz(m):
+        return np.where(m >= brk_mel, brk_hz * np.exp(logstep * (m - brk_mel)), f_sp * m)
+
+    edges = mel2hz(np.linspace(hz2mel(float(fmin)), hz2mel(float(fmax)), n_mels + 2))   # band edges in Hz
+    bins = np.linspace(0.0, sr / 2.0, n_fft // 2 + 1)
+    width = np.diff(edges)
+    rising = (bins[None, :] - edges[:-2, None]) / width[:-1, None]
+    falling = (edges[2:, None] - bins[None, :]) / width[1:, None]
+    fb = np.maximum(0.0, np.minimum(rising, falling)).astype(np.float32)
+    fb *= (2.0 / (edges[2:] - edges[:-2]))[:, None]
+    return fb
+
+
+class _MelHandle:
+    """Owns one e2e_mel* (device-side window, twiddles and sparse filterbank) on one CUDA device."""
+
+    def __init__(self, n_fft: int, hop: int, win: int, n_mels: int, basis: np.ndarray, device: torch.device):
+        self.device = device
+        basis = np.ascontiguousarray(basis, dtype=np.float32)
+        h = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            rc = _native.lib().e2e_mel_create(n_fft, hop, win, n_mels,
+                                              basis.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), ctypes.byref(h))
+        _native.check(rc, "e2e_mel_create")
+        self.h = h
+        self.n_mels = n_mels
+
+    def num_frames(self, L: int) -> int:
+        return int(_native.lib().e2e_mel_num_frames(self.h, L))
+
+    def run(self, wav: torch.Tensor, want_energy: bool, check_range: bool):
+        B, L = wav.shape
+        T = self.num_frames(L)
+        if T < 1:
+            raise ValueError("input too short: need more than %d samples" % 384)
+        dev = wav.device
+        mel = torch.empty((B, self.n_mels, T), dtype=torch.float32, device=dev)
+        energy = torch.empty((B, T), dtype=torch.float32, device=dev) if want_energy else None
+        flag = torch.zeros(1, dtype=torch.int32, device=dev) if check_range else None
+        with torch.cuda.device(dev):
+            rc = _native.lib().e2e_mel_forward(self.h, wav.data_ptr(), B, L, wav.stride(0), mel.data_ptr(),
+                                               energy.data_ptr() if want_energy else None,
+                                               flag.data_ptr() if check_range else None,
+                                               torch.cuda.current_stream(dev).cuda_stream)
+        _native.check(rc, "e2e_mel_forward")
+        return mel, energy, flag
+
+    def __del__(self):
+        try:
+            if self.h:
+                _native.lib().e2e_mel_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def _prepare(x: torch.Tensor) -> Tuple[torch.Tensor, bool]:
+    """[B, L] float32 on a CUDA device, unit stride along L.  Returns (tensor, came_from_cpu)."""
+    if not isinstance(x, torch.Tensor) or x.dim() != 2:
+        raise ValueError("expected a [B, L] tensor")
+    was_cpu = not x.is_cuda
+    if was_cpu:
+        if not torch.cuda.is_available():
+            raise RuntimeError("e2e_tts_b200 mel front-end needs a CUDA (sm_100a) device; there is no CPU path")
+        x = x.detach().to(torch.float32)
+        x = (x if x.is_pinned() else x.contiguous()).to("cuda", non_blocking=True)
+    else:
+        x = x.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+    if x.shape[1] > 1 and x.stride(1) != 1:
+        x = x.contiguous()
+    return x, was_cpu
+
+
+class TorchSTFT(nn.Module):
+    """stft.py:11-89.  Same constructor (positional use at dataloader.py:82-86) and public attributes."""
+
+    def __init__(self, filter_length=1024, hop_length=256, win_length=1024, n_mel_channels=80, sampling_rate=22050,
+                 mel_fmin=0.0, mel_fmax=8000.0, device=None):
+        super().__init__()
+        self.device = "cpu" if device is None else device
+        self.sampling_rate = sampling_rate
+        self.n_mel_channels = n_mel_channels
+        self.filter_length = filter_length
+        self.hop_length = hop_length
+        self.win_length = win_length
+        self.fmin = mel_fmin
+        self.fmax = mel_fmax
+        self.stft_pad = (int((filter_length - hop_length) / 2), int((filter_length - hop_length) / 2))
+        basis = slaney_mel_filterbank(sampling_rate, filter_length, n_mel_channels, mel_fmin, mel_fmax)
+        self.register_buffer("mel_basis", torch.from_numpy(basis).float())
+        self.window = torch.hann_window(win_length).to(self.device)
+        self._handles: Dict[str, _MelHandle] = {}
+
+    def _handle(self, device: torch.device) -> _MelHandle:
+        key = str(device)
+        h = self._handles.get(key)
+        if h is None:
+            h = _MelHandle(self.filter_length, self.hop_length, self.win_length, self.n_mel_channels,
+                           self.mel_basis.detach().cpu().numpy(), device)
+            self._handles[key] = h
+        return h
+
+    def mel_spectrogram(self, input_data, center=False, return_energy=False, check_range=True):
+        """stft.py:46-89.  input_data: [B, L] in [-1, 1] -> log-mel [B, n_mel_channels, T] (and energy [B, T]).
+        Raises AssertionError for out-of-range samples like the reference (:56-57); `check_range=False` skips
+        the (synchronising) flag read."""
+        if center:
+            raise NotImplementedError("center=True is not used by any e2e-tts caller and is not implemented")
+        x, was_cpu = _prepare(input_data)
+        mel, energy, flag = self._handle(x.device).run(x, return_energy, check_range)
+        if check_range:
+            assert int(flag.item()) == 0, "input samples must lie in [-1, 1]"
+        if was_cpu:
+            mel = mel.cpu()
+            energy = energy.cpu() if energy is not None else None
+        if return_energy is True:
+            return mel, energy
+        return mel
+
+
+_GM_HANDLES: Dict[tuple, _MelHandle] = {}
+
+
+def generate_melspecs(y, n_fft=1024, num_mels=80, sampling_rate=22050, hop_size=256, win_size=1024, fmin=0.0,
+                      fmax=8000.0, center=False) -> torch.Tensor:
+    """stft.py:107-135: functional twin of TorchSTFT.mel_spectrogram that only WARNS on out-of-range input."""
+    if center:
+        raise NotImplementedError("center=True is not used by any e2e-tts caller and is not implemented")
+    x, was_cpu = _prepare(y)
+    key = (n_fft, num_mels, sampling_rate, hop_size, win_size, float(fmin), None if fmax is None else float(fmax),
+           str(x.device))
+    h = _GM_HANDLES.get(key)
+    if h is None:
+        h = _MelHandle(n_fft, hop_size, win_size, num_mels,
+                       slaney_mel_filterbank(sampling_rate, n_fft, num_mels, fmin, fmax), x.device)
+        _GM_HANDLES[key] = h
+    mel, _, flag = h.run(x, False, True)
+    if int(flag.item()) != 0:
+        warnings.warn("input has samples outside [-1, 1] (min %g, max %g)" % (float(x.min()), float(x.max())))
+    return mel.cpu() if was_cpu else mel

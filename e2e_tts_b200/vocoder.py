@@ -1,0 +1,297 @@
+"""Drop-in HiFi-GAN generator for the e2e-tts synthesis path, running on hand-written sm_100a kernels.
+
+Mirrors the reference's public contract (e2e_tts/models/vocoder/generator.py:13-62, layers.py:10-69,
+function.py:4-17) as seen by its callers (e2e_tts/src/api/utils.py:53-56,144-145 and
+e2e_tts/src/tools/tools_for_model.py:45-54,94-140):
+
+    voc = HifiGan(config["models"]["hifigan"]); voc.load_state_dict(ckpt["state_dict"]); voc.eval().to("cuda")
+    wav = voc(mel.transpose(1, 2))            # [B, 80, T] fp32 (any strides) -> [B, 1, 256*T] fp32
+
+The module owns parameters with the reference's state-dict names (`*.weight_g`, `*.weight_v`, `*.bias`; or
+`*.weight` after remove_weight_norm()), so checkpoints load unchanged.  forward() is inference-only: it folds
+weight-norm once, packs bf16 GEMM-layout weights through the C ABI, and enqueues the CUDA kernels on the current
+torch stream without synchronising.  There is no CPU path and no fallback: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+
+from . import _native
+
+LRELU_SLOPE = 0.1  # generator.py:10, layers.py:7
+
+
+def get_padding(kernel_size: int, dilation: int = 1) -> int:
+    """function.py:16-17."""
+    return int((kernel_size * dilation - dilation) / 2)
+
+
+def init_weights(m, mean: float = 0.0, std: float = 0.01) -> None:
+    """function.py:4-7.  (On a weight-normed conv this writes the derived `.weight`, which the reference's
+    pre-forward hook overwrites, so it has no effect there either; kept for API parity.)"""
+    classname = m.__class__.__name__
+    if classname.find("Conv") != -1 and hasattr(m, "weight") and isinstance(m.weight, torch.Tensor):
+        m.weight.data.normal_(mean, std)
+
+
+class _WNConv(nn.Module):
+    """Parameter holder with the reference's weight-norm naming.  `transposed` selects ConvTranspose1d's
+    [C_in, C_out, k] weight layout (weight-norm dim 0 is then C_in)."""
+
+    def __init__(self, cin: int, cout: int, k: int, transposed: bool = False) -> None:
+        super().__init__()
+        self.cin, self.cout, self.k, self.transposed = cin, cout, k, transposed
+        shape = (cin, cout, k) if transposed else (cout, cin, k)
+        v = torch.empty(shape)
+        # PyTorch's default Conv init (kaiming_uniform(a=sqrt(5)) == U(+-1/sqrt(fan_in))): the reference's
+        # effective random init.  fan_in follows torch: weight.size(1) * k.
+        fan_in = shape[1] * k
+        bound = 1.0 / math.sqrt(fan_in)
+        nn.init.uniform_(v, -bound, bound)
+        self.weight_v = nn.Parameter(v)
+        self.weight_g = nn.Parameter(v.detach().reshape(shape[0], -1).norm(dim=1).reshape(shape[0], 1, 1).clone())
+        self.bias = nn.Parameter(torch.empty(cout).uniform_(-bound, bound))
+
+    def folded_weight(self) -> torch.Tensor:
+        """w = g * v / ||v||, norm over all dims but 0 (torch._weight_norm, SURVEY.md §8 a'4), in fp32."""
+        if "weight" in self._parameters:
+            return self.weight.detach().float()
+        v = self.weight_v.detach().float()
+        g = self.weight_g.detach().float()
+        n = v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, 1, 1)
+        return v * (g / n)
+
+    def remove_weight_norm(self) -> None:
+        if "weight" in self._parameters:
+            raise ValueError("weight_norm of this layer was already removed")
+        w = self.folded_weight()
+        dev = self.weight_v.device
+        del self._parameters["weight_g"]
+        del self._parameters["weight_v"]
+        self.weight = nn.Parameter(w.to(dev))
+
+
+class ResBlock1(nn.Module):
+    """layers.py:10-46 — 3 x [lrelu -> conv(k, d_i) -> lrelu -> conv(k, 1) -> + x]."""
+
+    def __init__(self, channels: int, kernel_size: int = 3, dilation=(1, 3, 5)) -> None:
+        super().__init__()
+        self.channels, self.kernel_size, self.dilation = channels, kernel_size, tuple(dilation)
+        self.convs1 = nn.ModuleList([_WNConv(channels, channels, kernel_size) for _ in self.dilation])
+        self.convs2 = nn.ModuleList([_WNConv(channels, channels, kernel_size) for _ in self.dilation])
+
+    def remove_weight_norm(self) -> None:
+        for layer in self.convs1:
+            layer.remove_weight_norm()
+        for layer in self.convs2:
+            layer.remove_weight_norm()
+
+
+class ResBlock2(nn.Module):
+    """layers.py:49-69 — 2 x [lrelu -> conv(k, d_i) -> + x]."""
+
+    def __init__(self, channels: int, kernel_size: int = 3, dilation=(1, 3)) -> None:
+        super().__init__()
+        # the reference builds exactly two convs from dilation[0] and dilation[1] (layers.py:52-57)
+        self.channels, self.kernel_size, self.dilation = channels, kernel_size, tuple(dilation)[:2]
+        self.convs = nn.ModuleList([_WNConv(channels, channels, kernel_size) for _ in self.dilation])
+
+    def remove_weight_norm(self) -> None:
+        for layer in self.convs:
+            layer.remove_weight_norm()
+
+
+class HifiGan(nn.Module):
+    """generator.py:13-62 on B200.  `config` is the `hifigan:` mapping of model_config.yaml:75-82."""
+
+    def __init__(self, config: dict) -> None:
+        super().__init__()
+        self.config = dict(config)
+        self.num_kernels = len(config["resblock_kernel_sizes"])
+        self.num_upsamples = len(config["upsample_rates"])
+        c0 = int(config["upsample_initial_channel"])
+        self.in_channels = 80  # hard-coded at generator.py:18
+        self.conv_pre = _WNConv(self.in_channels, c0, 7)
+        self._resblock_type = 1 if config["resblock"] == 1 else 2  # generator.py:19
+        resblock = ResBlock1 if self._resblock_type == 1 else ResBlock2
+        self.ups = nn.ModuleList()
+        for i, (u, k) in enumerate(zip(config["upsample_rates"], config["upsample_kernel_sizes"])):
+            self.ups.append(_WNConv(c0 // (2 ** i), c0 // (2 ** (i + 1)), int(k), transposed=True))
+        self.resblocks = nn.ModuleList()
+        ch = c0
+        for i in range(len(self.ups)):
+            ch = c0 // (2 ** (i + 1))
+            for k, d in zip(config["resblock_kernel_sizes"], config["resblock_dilation_sizes"]):
+                self.resblocks.append(resblock(ch, int(k), tuple(int(x) for x in d)))
+        self.conv_post = _WNConv(ch, 1, 7)
+        self.hop = 1
+        for u in config["upsample_rates"]:
+            self.hop *= int(u)
+        self._handle = None          # e2e_voc* (created lazily on the first CUDA forward)
+        self._handle_device = None
+        self._loaded_version = None  # parameter-version fingerprint the packed weights correspond to
+        self._workspaces: Dict[tuple, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------ state-dict compatibility
+    def _wn_layers(self) -> List[tuple]:
+        out = [("conv_pre", self.conv_pre)]
+        for i, l in enumerate(self.ups):
+            out.append(("ups.%d" % i, l))
+        for n, rb in enumerate(self.resblocks):
+            if isinstance(rb, ResBlock1):
+                for m, l in enumerate(rb.convs1):
+                    out.append(("resblocks.%d.convs1.%d" % (n, m), l))
+                for m, l in enumerate(rb.convs2):
+                    out.append(("resblocks.%d.convs2.%d" % (n, m), l))
+            else:
+                for m, l in enumerate(rb.convs):
+                    out.append(("resblocks.%d.convs.%d" % (n, m), l))
+        out.append(("conv_post", self.conv_post))
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        """Accepts the reference's 234-key weight_g/weight_v/bias layout (utils.py:54-55) and also the folded
+        `*.weight` layout a checkpoint saved after remove_weight_norm() has."""
+        sd = dict(state_dict)
+        for name, layer in self._wn_layers():
+            wkey = name + ".weight"
+            has_wn = "weight_v" in layer._parameters
+            if wkey in sd and has_wn:
+                w = sd.pop(wkey).detach().float()
+                sd[name + ".weight_v"] = w
+                sd[name + ".weight_g"] = w.reshape(w.shape[0], -1).norm(dim=1).reshape(-1, 1, 1)
+            elif (name + ".weight_v") in sd and not has_wn:
+                v = sd.pop(name + ".weight_v").detach().float()
+                g = sd.pop(name + ".weight_g").detach().float()
+                sd[wkey] = v * (g / v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, 1, 1))
+        res = super().load_state_dict(sd, strict=strict, **kw)
+        self._loaded_version = None
+        return res
+
+    def remove_weight_norm(self) -> None:
+        """generator.py:55-62 (output unchanged; the packed weights were folded anyway)."""
+        print("Removing weight norm...")
+        for layer in self.ups:
+            layer.remove_weight_norm()
+        for layer in self.resblocks:
+            layer.remove_weight_norm()
+        self.conv_pre.remove_weight_norm()
+        self.conv_post.remove_weight_norm()
+        self._loaded_version = None
+
+    # ------------------------------------------------------------------ native side
+    def _native_config(self) -> _native.VocConfig:
+        c = self.config
+        cfg = _native.VocConfig()
+        cfg.in_channels = self.in_channels
+        cfg.upsample_initial_channel = int(c["upsample_initial_channel"])
+        cfg.resblock = self._resblock_type
+        cfg.num_upsamples = self.num_upsamples
+        if self.num_upsamples > _native.E2E_MAX_UPSAMPLES or self.num_kernels > _native.E2E_MAX_KERNELS:
+            raise ValueError("too many upsample stages / resblock kernels")
+        for i, (u, k) in enumerate(zip(c["upsample_rates"], c["upsample_kernel_sizes"])):
+            cfg.upsample_rates[i] = int(u)
+            cfg.upsample_kernel_sizes[i] = int(k)
+        cfg.num_kernels = self.num_kernels
+        for j, (k, d) in enumerate(zip(c["resblock_kernel_sizes"], c["resblock_dilation_sizes"])):
+            d = list(d)
+            if self._resblock_type != 1:
+                d = d[:2] if len(d) >= 2 else d  # ResBlock2 is built from dilation[0], dilation[1] (layers.py:52-57)
+            if len(d) > _native.E2E_MAX_DILATIONS:
+                raise ValueError("too many dilations")
+            cfg.resblock_kernel_sizes[j] = int(k)
+            cfg.num_dilations[j] = len(d)
+            for m, x in enumerate(d):
+                cfg.resblock_dilation_sizes[j][m] = int(x)
+        return cfg
+
+    def _version_fingerprint(self, device) -> tuple:
+        return (str(device),) + tuple((id(p), p._version) for p in self.parameters())
+
+    def _sync_native(self, device: torch.device) -> None:
+        L = _native.lib()
+        if self._handle is not None and self._handle_device != device:
+            L.e2e_voc_destroy(self._handle)
+            self._handle = None
+            self._workspaces.clear()
+        if self._handle is None:
+            h = ctypes.c_void_p()
+            cfg = self._native_config()
+            _native.check(L.e2e_voc_create(ctypes.byref(cfg), ctypes.byref(h)), "e2e_voc_create")
+            self._handle = h
+            self._handle_device = device
+            self._loaded_version = None
+        fp = self._version_fingerprint(device)
+        if self._loaded_version == fp:
+            return
+        for name, layer in self._wn_layers():
+            w = layer.folded_weight().cpu().contiguous()
+            b = layer.bias.detach().float().cpu().contiguous()
+            _native.check(
+                L.e2e_voc_load_layer(self._handle, name.encode(),
+                                     ctypes.cast(w.data_ptr(), ctypes.POINTER(ctypes.c_float)), w.numel(),
+                                     ctypes.cast(b.data_ptr(), ctypes.POINTER(ctypes.c_float)), b.numel()),
+                "e2e_voc_load_layer(%s)" % name)
+        if L.e2e_voc_missing_layers(self._handle) != 0:
+            raise _native.NativeError("not every generator layer received weights")
+        self._loaded_version = fp
+
+    def launches_per_forward(self) -> int:
+        if self._handle is None:
+            raise RuntimeError("call forward() once first")
+        return int(_native.lib().e2e_voc_launches_per_forward(self._handle))
+
+    def _workspace(self, B: int, T: int, device: torch.device) -> torch.Tensor:
+        key = (B, T, str(device))
+        ws = self._workspaces.get(key)
+        if ws is None:
+            nbytes = int(_native.lib().e2e_voc_workspace_bytes(self._handle, B, T))
+            if nbytes == 0:
+                raise _native.NativeError("e2e_voc_workspace_bytes returned 0")
+            if len(self._workspaces) >= 4:
+                self._workspaces.clear()
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            self._workspaces[key] = ws
+        return ws
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """generator.py:37-53.  x: [B, 80, T] float32 CUDA tensor (non-contiguous views are fine)."""
+        if not isinstance(x, torch.Tensor) or x.dim() != 3 or x.shape[1] != self.in_channels:
+            raise ValueError("expected a [B, %d, T] tensor, got %s" % (self.in_channels, tuple(getattr(x, "shape", ()))))
+        if not x.is_cuda:
+            raise RuntimeError("e2e_tts_b200.HifiGan runs on CUDA (sm_100a) only: move the module and its input "
+                               "to a B200 device; there is no CPU path")
+        if x.dtype != torch.float32:
+            raise ValueError("expected float32 input, got %s" % x.dtype)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise RuntimeError("e2e_tts_b200.HifiGan is inference-only; call it under torch.no_grad()")
+        B, _, T = x.shape
+        if B == 0 or T == 0:
+            return x.new_zeros((B, 1, self.hop * T))
+        p0 = next(self.parameters())
+        if p0.device != x.device:
+            raise RuntimeError("module parameters are on %s but the input is on %s" % (p0.device, x.device))
+        with torch.cuda.device(x.device):
+            self._sync_native(x.device)
+            ws = self._workspace(B, T, x.device)
+            ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+            out = torch.empty((B, 1, self.hop * T), dtype=torch.float32, device=x.device)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            rc = _native.lib().e2e_voc_forward(self._handle, x.data_ptr(), x.stride(0), x.stride(1), x.stride(2),
+                                               B, T, out.data_ptr(), ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()),
+                                               stream)
+            _native.check(rc, "e2e_voc_forward")
+        return out
+
+    def __del__(self):
+        try:
+            if self._handle is not None:
+                _native.lib().e2e_voc_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass

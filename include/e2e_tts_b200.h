@@ -1,0 +1,106 @@
+/*
+ * e2e_tts_b200 — C ABI of the B200-native synthesis hot path of InterlinkLabs/e2e-tts.
+ *
+ * The reference has no FFI: its "plugin API" for this path is the duck-typed Python contract
+ *   HifiGan(config).forward(mel[B,80,T]) -> wav[B,1,256*T]      e2e_tts/models/vocoder/generator.py:13-53
+ *   TorchSTFT(...).mel_spectrogram(wav[B,L]) -> mel[B,80,T]      e2e_tts/src/tools/stft.py:11-89
+ *   generate_melspecs(y, ...)                                    e2e_tts/src/tools/stft.py:107-135
+ * called from e2e_tts/src/api/utils.py:53-56,144-145 and e2e_tts/src/tools/tools_for_data.py:114,178.
+ * The Python mirror of that contract (package e2e_tts_b200) binds exactly the entry points below with ctypes;
+ * INTEGRATION.md shows the stub.  Plain pointers and sizes only, no torch types, no exceptions across the
+ * boundary.  Every function returns 0 on success, a negative value for a bad argument / unsupported
+ * configuration, or a positive cudaError_t; e2e_last_error_string() describes the last failure of the
+ * calling thread.  All device pointers must belong to the current CUDA device; work is enqueued on `stream`
+ * (a cudaStream_t passed as void*) and never synchronises the host.
+ */
+#ifndef E2E_TTS_B200_H
+#define E2E_TTS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define E2E_MAX_UPSAMPLES 8
+#define E2E_MAX_KERNELS 8
+#define E2E_MAX_DILATIONS 8
+
+/* Mirrors the `hifigan:` mapping of e2e_tts/config/model_config.yaml:75-82 as consumed by
+ * HifiGan.__init__ (generator.py:14-35). */
+typedef struct e2e_voc_config {
+  int32_t in_channels;              /* 80, hard-coded at generator.py:18 */
+  int32_t upsample_initial_channel; /* 512 */
+  int32_t resblock;                 /* 1 -> ResBlock1 (layers.py:10-46), anything else -> ResBlock2 (layers.py:49-69) */
+  int32_t num_upsamples;
+  int32_t upsample_rates[E2E_MAX_UPSAMPLES];
+  int32_t upsample_kernel_sizes[E2E_MAX_UPSAMPLES];
+  int32_t num_kernels;
+  int32_t resblock_kernel_sizes[E2E_MAX_KERNELS];
+  int32_t num_dilations[E2E_MAX_KERNELS];
+  int32_t resblock_dilation_sizes[E2E_MAX_KERNELS][E2E_MAX_DILATIONS];
+} e2e_voc_config;
+
+typedef struct e2e_voc e2e_voc; /* opaque: packed bf16 weights + launch plans of one generator */
+
+/* Replaces HifiGan.__init__ (generator.py:14-35).  Allocates device memory for the packed weights. */
+int e2e_voc_create(const e2e_voc_config* cfg, e2e_voc** out);
+void e2e_voc_destroy(e2e_voc* v);
+
+/* Replaces load_state_dict for one layer (e2e_tts/src/api/utils.py:54-55).  `name` is the reference's
+ * state-dict prefix: "conv_pre", "ups.<i>", "resblocks.<n>.convs1.<m>", "resblocks.<n>.convs2.<m>",
+ * "resblocks.<n>.convs.<m>" (ResBlock2), "conv_post".  `weight` is the FOLDED fp32 weight on the HOST in the
+ * reference's own layout (Conv1d [C_out][C_in][k]; ConvTranspose1d [C_in][C_out][k]), i.e. g*v/||v|| already
+ * applied (generator.py:55-62 semantics); `bias` is [C_out] fp32 on the host.  The call rearranges the weight
+ * into GEMM columns, rounds to bf16, swizzles and uploads it (synchronous; not a hot-path call). */
+int e2e_voc_load_layer(e2e_voc* v, const char* name, const float* weight, int64_t weight_numel, const float* bias,
+                       int64_t bias_numel);
+
+/* Number of layers that still lack weights (0 = ready for e2e_voc_forward). */
+int e2e_voc_missing_layers(const e2e_voc* v);
+
+/* Device scratch needed by e2e_voc_forward for a [B,80,T] input. */
+size_t e2e_voc_workspace_bytes(const e2e_voc* v, int32_t B, int32_t T);
+
+/* Replaces HifiGan.forward (generator.py:37-53).  mel: device fp32, element (b,c,t) at mel[b*sB + c*sC + t*sT]
+ * (any strides: the reference passes a transposed view, utils.py:144).  wav: device fp32 [B][upsample*T]
+ * contiguous (= [B,1,256*T]).  workspace: device, >= e2e_voc_workspace_bytes, 1024-byte aligned. */
+int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B, int32_t T,
+                    float* wav, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Total upsampling factor (product of upsample_rates; 256 for the default config). */
+int e2e_voc_hop(const e2e_voc* v);
+
+/* Kernel launches enqueued by one e2e_voc_forward call at the current configuration. */
+int e2e_voc_launches_per_forward(const e2e_voc* v);
+
+/* ---- mel front-end ---- */
+typedef struct e2e_mel e2e_mel; /* opaque: window, twiddles and the sparse mel filterbank on the device */
+
+/* Replaces TorchSTFT.__init__ (stft.py:12-44).  `mel_basis` is the dense [n_mels][n_fft/2+1] fp32 filterbank
+ * on the HOST (the reference gets it from librosa.filters.mel, stft.py:34-40).  Supported: n_fft == win_length
+ * == 1024, hop_length == 256 (the reference's preprocessing_config.yaml:5-8), n_mels <= 128. */
+int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_length, int32_t n_mels, const float* mel_basis,
+                   e2e_mel** out);
+void e2e_mel_destroy(e2e_mel* m);
+
+/* Frames produced for L samples: 1 + (L + 2*pad - n_fft) / hop with pad = (n_fft - hop)/2 (stft.py:33,60-76). */
+int64_t e2e_mel_num_frames(const e2e_mel* m, int64_t L);
+
+/* Replaces TorchSTFT.mel_spectrogram / generate_melspecs (stft.py:46-89,107-135).  wav: device fp32, row b at
+ * wav + b*ldw, L valid samples (L > pad).  mel: device fp32 [B][n_mels][T].  energy: device fp32 [B][T] or
+ * NULL.  range_flag: device int32 (or NULL); set to 1 if any sample is outside [-1, 1] (the reference asserts,
+ * stft.py:56-57; the caller reads the flag after the stream is synchronised and raises). */
+int e2e_mel_forward(e2e_mel* m, const float* wav, int32_t B, int64_t L, int64_t ldw, float* mel, float* energy,
+                    int32_t* range_flag, void* stream);
+
+const char* e2e_last_error_string(void);
+
+/* Library / build identification, e.g. "e2e_tts_b200 0.1 sm_100a". */
+const char* e2e_version_string(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E2E_TTS_B200_H */

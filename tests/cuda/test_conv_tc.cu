@@ -33,14 +33,13 @@ struct Cfg {
   int u;                            // polyphase upsample factor (dil == 0)
   int B, T, mt;
   int res, sum, div3, f32out, actout;
-  int base_off_mode;
+  int reserved;
 };
 
 static const Cfg kCfgs[] = {
     {"gemm64 1tap", 64, 64, 64, 1, 1, 0, 1, 128, 1, 0, 0, 0, 1, 0, 0},
     {"c64 k3 d8 (shift mult of 8)", 64, 64, 64, 3, 8, 0, 2, 300, 1, 0, 0, 0, 1, 1, 0},
     {"c64 k3 d1 (odd row shift)", 64, 64, 64, 3, 1, 0, 2, 300, 1, 0, 0, 0, 1, 1, 0},
-    {"c64 k3 d1 base_off", 64, 64, 64, 3, 1, 0, 2, 300, 1, 0, 0, 0, 1, 1, 1},
     {"c128 k11 d5 mt2 res", 128, 128, 128, 11, 5, 0, 3, 1000, 2, 1, 0, 0, 1, 1, 0},
     {"c128 k7 d3 mt2 res sum div3", 128, 128, 128, 7, 3, 0, 2, 777, 2, 1, 1, 1, 0, 1, 0},
     {"c256 k11 d5 mt2", 256, 256, 256, 11, 5, 0, 2, 700, 2, 1, 0, 0, 1, 1, 0},
@@ -201,8 +200,7 @@ int main(int argc, char** argv) {
   p.out_f32 = dout;
   p.out_act = dact;
   p.slope = 0.1f;
-  p.div3 = c.div3;
-  p.base_off_mode = c.base_off_mode;
+  p.divisor = c.div3 ? 3.0f : 0.f;
   printf("  plan: grid=(%d,%d,%d) smem=%d mt=%d slab_rows=%d box=%d stages=%d stage_bytes=%d chunks=%d tmem=%d hl=%d\n",
          plan.grid.x, plan.grid.y, plan.grid.z, plan.smem_bytes, p.mt, p.slab_rows, p.box_rows, p.n_stages,
          p.stage_bytes, p.n_chunks, p.tmem_cols, p.hl);

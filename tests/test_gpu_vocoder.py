@@ -1,0 +1,123 @@
+"""GPU parity tests for the vocoder path, through the C ABI (e2e_voc_forward) via the drop-in module.
+
+Tolerance (bf16 operands, fp32 accumulate and fp32 residual stream, vs the fp32 reference/oracle):
+    max |wav - ref| <= 2e-2 * max|ref|     and     mean |wav - ref| <= 3e-3 * max|ref|
+also enforced separately on the first / last 4096 samples, where per-layer zero padding matters."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import e2e_tts_b200 as pkg
+from oracle import hifigan_oracle as ho
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MAX_TOL, MEAN_TOL = 2e-2, 3e-3
+
+
+def mel_like(B, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(B, 80, T, generator=g) * 2.0 - 5.0).clamp(-11.5, 2.0)
+
+
+def check(got, want, what=""):
+    got, want = got.float().cpu(), want.float().cpu()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    assert torch.isfinite(got).all()
+    scale = want.abs().max().item()
+    def one(a, b, tag):
+        d = (a - b).abs()
+        assert d.max().item() <= MAX_TOL * scale, "%s %s: max err %.3g vs scale %.3g" % (what, tag, d.max().item(), scale)
+        assert d.mean().item() <= MEAN_TOL * scale, "%s %s: mean err %.3g vs scale %.3g" % (what, tag, d.mean().item(), scale)
+    one(got, want, "all")
+    n = min(4096, got.shape[-1])
+    one(got[..., :n], want[..., :n], "head")
+    one(got[..., -n:], want[..., -n:], "tail")
+
+
+def build(cfg, seed, regime):
+    sd = ho.make_state_dict(cfg, seed, regime)
+    voc = pkg.HifiGan(cfg)
+    voc.load_state_dict(sd)
+    return voc.eval().to("cuda"), sd
+
+
+@pytest.mark.parametrize("name", ["voc_default_init", "voc_strong_init", "voc_strong_resblock2"])
+def test_against_reference_golden(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg = dict(ho.DEFAULT_CONFIG)
+    cfg["resblock"] = int(g["resblock"])
+    voc, _ = build(cfg, int(g["seed"]), str(g["regime"]))
+    with torch.no_grad():
+        wav = voc(torch.from_numpy(g["mel"]).cuda())
+    assert wav.is_cuda and wav.dtype == torch.float32
+    check(wav, torch.from_numpy(g["wav"]), name)
+
+
+@pytest.mark.parametrize("B,T,regime", [(1, 1, "strong"), (3, 7, "strong"), (2, 130, "strong"), (1, 431, "default"),
+                                        (2, 431, "strong")])
+def test_against_oracle(B, T, regime):
+    cfg = ho.DEFAULT_CONFIG
+    voc, sd = build(cfg, 40 + T, regime)
+    mel = mel_like(B, T, 7 * T + B)
+    with torch.no_grad():
+        want = ho.hifigan_forward(sd, cfg, mel)
+        got = voc(mel.cuda())
+    assert tuple(got.shape) == (B, 1, 256 * T)
+    check(got, want, "B%d T%d %s" % (B, T, regime))
+
+
+def test_transposed_view_input_and_call_site_contract():
+    """utils.py:144-145: vocoder(mel_predicted.transpose(1, 2)).squeeze(1).detach().cpu().numpy()"""
+    cfg = ho.DEFAULT_CONFIG
+    voc, sd = build(cfg, 5, "strong")
+    mel_btc = mel_like(2, 40, 99).transpose(1, 2).contiguous()          # [B, T, 80] as the acoustic model emits
+    with torch.no_grad():
+        audio = voc(mel_btc.cuda().transpose(1, 2)).squeeze(1).detach().cpu().numpy()
+        want = ho.hifigan_forward(sd, cfg, mel_btc.transpose(1, 2))
+    assert audio.shape == (2, 40 * 256)
+    check(torch.from_numpy(audio)[:, None], want, "transposed view")
+
+
+def test_batch_items_are_independent_and_deterministic():
+    cfg = ho.DEFAULT_CONFIG
+    voc, _ = build(cfg, 6, "strong")
+    mel = mel_like(3, 50, 1).cuda()
+    with torch.no_grad():
+        a = voc(mel)
+        b = voc(mel[1:2])
+        c = voc(mel)
+    assert torch.equal(a, c)
+    assert torch.equal(a[1:2], b)
+
+
+def test_long_form_tile_seams():
+    """30 s utterance (config 3 shape, one item): compare a window around every 128*mt-row tile seam."""
+    cfg = ho.DEFAULT_CONFIG
+    voc, sd = build(cfg, 8, "strong")
+    T = 2584
+    mel = mel_like(1, T, 2)
+    with torch.no_grad():
+        got = voc(mel.cuda()).cpu()
+        want = ho.hifigan_forward(sd, cfg, mel)
+    check(got, want, "long")
+    d = (got - want).abs()[0, 0]
+    scale = want.abs().max().item()
+    for seam in range(512, d.numel(), 512):                              # every possible output-tile boundary
+        assert d[seam - 8: seam + 8].max().item() <= MAX_TOL * scale
+
+
+def test_weights_reload_after_in_place_update():
+    cfg = ho.DEFAULT_CONFIG
+    voc, _ = build(cfg, 9, "strong")
+    mel = mel_like(1, 12, 3).cuda()
+    with torch.no_grad():
+        a = voc(mel)
+        sd2 = ho.make_state_dict(cfg, 10, "strong")
+        voc.load_state_dict(sd2)
+        b = voc(mel)
+        want = ho.hifigan_forward(sd2, cfg, mel.cpu())
+    assert not torch.equal(a, b)
+    check(b, want, "reloaded")
