@@ -1,0 +1,123 @@
+"""GPU parity tests for the STFT -> mel path, through the C ABI (e2e_mel_forward) via the drop-in TorchSTFT.
+
+Tolerances (fp32 kernel vs the fp32 reference / oracle).  The error of an fp32 FFT is relative to the largest
+magnitude in the frame, so the bound is stated on the LINEAR mel per frame (the reference itself sits 2e-6 *
+frame-max away from a float64 evaluation, tests/test_oracle.py):
+    |mel_lin - ref_lin| <= 1e-5 * max_m ref_lin[:, t] + 1e-7      (exp of the log-mel, clamp floor applied)
+    mean |log-mel - ref|  <= 1e-4                                  (mel L1, the north-star metric)
+    |energy - ref| <= 2e-5 * ref
+    frame count and shapes exact."""
+import glob
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import e2e_tts_b200 as pkg
+from oracle import mel_oracle as mo
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def check(mel, energy, ref_mel, ref_energy, what=""):
+    mel, ref_mel = mel.double().cpu(), ref_mel.double().cpu()
+    assert mel.shape == ref_mel.shape, (mel.shape, ref_mel.shape)
+    assert torch.isfinite(mel).all()
+    lin, ref_lin = mel.exp(), ref_mel.exp()
+    bound = 1e-5 * ref_lin.max(dim=1, keepdim=True).values + 1e-7
+    excess = ((lin - ref_lin).abs() / bound).max().item()
+    assert excess <= 1.0, "%s: linear-mel error is %.2fx the bound" % (what, excess)
+    l1 = (mel - ref_mel).abs().mean().item()
+    assert l1 <= 1e-4, "%s: log-mel L1 %.3g" % (what, l1)
+    if energy is not None:
+        energy, ref_energy = energy.double().cpu(), ref_energy.double().cpu()
+        assert energy.shape == ref_energy.shape
+        rel = ((energy - ref_energy).abs() / ref_energy).max().item()
+        assert rel <= 2e-5, "%s: energy rel err %.3g" % (what, rel)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "mel_*.npz"))))
+def test_against_reference_golden(path):
+    g = np.load(path)
+    stft = pkg.TorchSTFT()
+    mel, energy = stft.mel_spectrogram(torch.from_numpy(g["wav"]).cuda(), return_energy=True)
+    assert mel.is_cuda and energy.is_cuda
+    check(mel, energy, torch.from_numpy(g["mel"]), torch.from_numpy(g["energy"]), os.path.basename(path))
+    mel_only = stft.mel_spectrogram(torch.from_numpy(g["wav"]).cuda())
+    assert torch.equal(mel_only, mel)
+
+
+def signals(B, L, seed):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(L).float() / 22050.0
+    noise = torch.rand(B, L, generator=g) * 2 - 1
+    f = 60.0 + 5000.0 * torch.rand(B, 5, 1, generator=g)
+    env = torch.rand(B, 1, generator=g)
+    speech = (torch.sin(2 * np.pi * f * t[None, None, :]) / 5.2).sum(1) * env
+    speech[:, L // 5: L // 5 + L // 5] = 0.0
+    return {"noise": noise, "speechlike": speech}
+
+
+@pytest.mark.parametrize("B,L", [(1, 385), (2, 1000), (3, 8192), (2, 110250), (2, 220500), (5, 33333)])
+def test_against_oracle(B, L):
+    stft = pkg.TorchSTFT()
+    for kind, wav in signals(B, L, L + B).items():
+        ref_mel, ref_energy = mo.mel_spectrogram(wav, return_energy=True)
+        mel, energy = stft.mel_spectrogram(wav.cuda(), return_energy=True)
+        assert mel.shape[-1] == mo.num_frames(L)
+        check(mel, energy, ref_mel, ref_energy, "%s B%d L%d" % (kind, B, L))
+        # and against the float64 definition
+        lm64, _, en64 = mo.mel_spectrogram_f64(wav.numpy())
+        check(mel, energy, torch.from_numpy(lm64), torch.from_numpy(en64), "f64 %s B%d L%d" % (kind, B, L))
+
+
+def test_cpu_in_cpu_out_like_the_reference_call_site():
+    """tools_for_data.py:113-115: audio_norm.unsqueeze(0) -> mel_spectrogram(...) -> melspec.squeeze(0).numpy()"""
+    wav = signals(1, 30000, 3)["speechlike"]
+    stft = pkg.TorchSTFT(1024, 256, 1024, 80, 22050, 0.0, 8000.0)
+    melspec, energy = stft.mel_spectrogram(wav, return_energy=True)
+    assert not melspec.is_cuda and not energy.is_cuda
+    ref_mel, ref_energy = mo.mel_spectrogram(wav, return_energy=True)
+    assert melspec.squeeze(0).numpy().shape == (80, mo.num_frames(30000))
+    check(melspec, energy, ref_mel, ref_energy, "cpu tensor")
+
+
+def test_silence_and_clamp_floor():
+    stft = pkg.TorchSTFT()
+    mel, energy = stft.mel_spectrogram(torch.zeros(2, 5000).cuda(), return_energy=True)
+    assert torch.allclose(mel.cpu(), torch.full(mel.shape, float(np.log(1e-5))))
+    assert torch.allclose(energy.cpu(), torch.full(energy.shape, float(np.sqrt(513e-9))), rtol=1e-5)
+
+
+def test_range_assertion_and_warning():
+    stft = pkg.TorchSTFT()
+    ok = torch.ones(1, 4096).cuda()
+    ok[0, ::2] = -1.0
+    stft.mel_spectrogram(ok)                                        # exactly +-1.0 is allowed (stft.py:56-57)
+    bad = torch.zeros(2, 4096).cuda()
+    bad[1, 4000] = 1.0001
+    with pytest.raises(AssertionError):
+        stft.mel_spectrogram(bad)
+    stft.mel_spectrogram(bad, check_range=False)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        out = pkg.generate_melspecs(bad)                            # only warns (stft.py:108-111)
+    assert len(w) == 1 and out.shape == (2, 80, 16)
+    with pytest.raises(ValueError):
+        stft.mel_spectrogram(torch.zeros(1, 384).cuda())            # reflect pad needs L > 384
+
+
+def test_generate_melspecs_matches_class_and_rows_are_independent():
+    wav = signals(4, 20000, 9)["noise"].cuda()
+    a = pkg.TorchSTFT().mel_spectrogram(wav)
+    b = pkg.generate_melspecs(wav)
+    assert torch.equal(a, b)
+    c = pkg.generate_melspecs(wav[2:3])
+    assert torch.equal(a[2:3], c)
+    strided = torch.zeros(4, 20480).cuda()
+    strided[:, :20000] = wav
+    d = pkg.TorchSTFT().mel_spectrogram(strided[:, :20000])         # row stride != L
+    assert torch.equal(a, d)
