@@ -52,6 +52,22 @@ struct ConvParams {
   __nv_bfloat16* out_act;  // bf16 [B][T][n_total] = leaky_relu(out, slope) or nullptr
 };
 
+#ifdef E2E_TRACE
+// Debug build only: per-CTA phase timestamps (globaltimer ns) for every 8th CTA, read back by tests/cuda.
+__device__ unsigned long long g_trace[512][12];
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define E2E_TR(slot)                                               \
+  do {                                                             \
+    if (trace_id >= 0) g_trace[trace_id][slot] = gtime_ns();       \
+  } while (0)
+#else
+#define E2E_TR(slot)
+#endif
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -76,6 +92,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
   const int t0 = blockIdx.x * (128 * p.mt);
   const int nti = blockIdx.y;
   const int b = blockIdx.z;
+#ifdef E2E_TRACE
+  const int lin_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  const int trace_id = (lin_ % 8 == 0 && lin_ / 8 < 512) ? lin_ / 8 : -1;
+  if (threadIdx.x == 0) {
+    E2E_TR(0);
+    if (trace_id >= 0) {
+      unsigned int smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      g_trace[trace_id][10] = smid;
+    }
+  }
+#endif
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_in);
@@ -95,6 +123,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) E2E_TR(1);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -107,6 +136,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
           tma_load_3d(slab + pn * panel_bytes + bx * p.box_rows * rowb, &tm_in, pn * ch_per_panel,
                       t0 - p.hl + bx * p.box_rows, b, &panel_full[pn]);
       }
+      E2E_TR(2);
       const uint8_t* wsrc = p.w + static_cast<size_t>(nti) * total_tiles * tile_bytes;
       for (int c = 0; c < p.n_chunks; ++c) {
         const int stage = c % p.n_stages;
@@ -119,6 +149,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
         bulk_load_1d(ring + stage * p.stage_bytes, wsrc + static_cast<size_t>(first) * tile_bytes, bytes,
                      &ring_full[stage]);
       }
+      E2E_TR(3);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -133,6 +164,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
         const uint32_t par = (c / p.n_stages) & 1;
         mbar_wait(&ring_full[stage], par, 0x200 + stage);
         tc_fence_after_sync();
+        if (c == 0) E2E_TR(4);
         const int ntile = min(p.tiles_per_chunk, total_tiles - c * p.tiles_per_chunk);
         for (int i = 0; i < ntile; ++i, ++tile) {
           const int pn = tile / p.taps;
@@ -140,6 +172,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
           if (tap == 0) {
             mbar_wait(&panel_full[pn], 0, 0x300 + pn);
             tc_fence_after_sync();
+            if (pn == 0) E2E_TR(5);
           }
           const int row0 = p.hl + p.shift[nti][tap];
           const uint32_t a_base = slab_addr + pn * panel_bytes + row0 * rowb;
@@ -155,6 +188,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
         }
         umma_commit(&ring_empty[stage]);  // frees the weight stage once these MMAs have read it
       }
+      E2E_TR(6);
       umma_commit(acc_full);
     }
   } else {
@@ -162,6 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
     const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31 are the ones this warp may read
     mbar_wait(acc_full, 0, 0x400);
     tc_fence_after_sync();
+    if (threadIdx.x == 64) E2E_TR(7);
     const int nchunk = p.nt / 32;
     for (int m = 0; m < p.mt; ++m) {
       const int t = t0 + m * 128 + quarter * 32 + lane;
@@ -228,12 +263,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
     }
   }
 
+  if (threadIdx.x == 64) E2E_TR(8);
   tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (threadIdx.x == 0) E2E_TR(9);
 }
 
 }  // namespace e2e

@@ -62,6 +62,7 @@ struct e2e_voc {
   int cin_pad = 0;
   int hop = 1;
   int n_sms = 148;
+  cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // one-shot profiling events
 };
 
 static int pick_nt(int cout) { return cout >= 256 ? 256 : cout; }
@@ -190,6 +191,13 @@ extern "C" void e2e_voc_destroy(e2e_voc* v) {
     if (L.d_bias) cudaFree(L.d_bias);
   }
   delete v;
+}
+
+extern "C" int e2e_voc_set_profile_events(e2e_voc* v, void* ev_begin, void* ev_end) {
+  if (!v) return fail(-1, "null argument");
+  v->ev_begin = reinterpret_cast<cudaEvent_t>(ev_begin);
+  v->ev_end = reinterpret_cast<cudaEvent_t>(ev_end);
+  return 0;
 }
 
 extern "C" int e2e_voc_hop(const e2e_voc* v) { return v ? v->hop : 0; }
@@ -443,7 +451,16 @@ extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t
   }
   Buffers bf;
   carve(v, B, T, workspace, bf);
-  for (const Op& op : it->second) {
+  const std::vector<Op>& ops = it->second;
+  size_t first_conv = ops.size(), last_conv = 0;
+  for (size_t i = 0; i < ops.size(); ++i)
+    if (ops[i].kind == 1) {
+      first_conv = i < first_conv ? i : first_conv;
+      last_conv = i;
+    }
+  for (size_t oi = 0; oi < ops.size(); ++oi) {
+    const Op& op = ops[oi];
+    if (oi == first_conv && v->ev_begin) cudaEventRecord(v->ev_begin, st);
     if (op.kind == 0) {
       const long long total = (long long)B * T * (v->cin_pad / 8);
       mel_to_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mel, sB, sC, sT, B, T, v->cfg.in_channels,
@@ -458,7 +475,9 @@ extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t
       post_conv_tanh_kernel<<<grid, 256, 0, st>>>(bf.Y, reinterpret_cast<const float*>(L.d_w), L.post_bias, B, Tout,
                                                   L.cin, L.k, wav);
     }
+    if (oi == last_conv && v->ev_end) cudaEventRecord(v->ev_end, st);
   }
+  v->ev_begin = v->ev_end = nullptr;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("e2e_voc_forward launch: ") + cudaGetErrorString(e));
   return 0;

@@ -69,6 +69,11 @@ size_t e2e_voc_workspace_bytes(const e2e_voc* v, int32_t B, int32_t T);
 int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B, int32_t T,
                     float* wav, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement hook: the NEXT e2e_voc_forward records `ev_begin` (a cudaEvent_t) on its stream just before its first
+ * tensor-core convolution launch and `ev_end` right after its last one, then forgets both (one-shot).  bench.py
+ * uses it to time the dominant kernel family inside the timed region.  Pass NULLs to cancel. */
+int e2e_voc_set_profile_events(e2e_voc* v, void* ev_begin, void* ev_end);
+
 /* Total upsampling factor (product of upsample_rates; 256 for the default config). */
 int e2e_voc_hop(const e2e_voc* v);
 

@@ -57,6 +57,9 @@ static const Cfg kCfgs[] = {
     {"perf c256 k11 d1 T3448", 256, 256, 256, 11, 1, 0, 16, 3448, 2, 1, 0, 0, 1, 1, 0},
     {"perf c64 k11 d1 T55168", 64, 64, 64, 11, 1, 0, 16, 55168, 4, 1, 0, 0, 1, 1, 0},
     {"perf c32 k11 d1 T110336", 32, 32, 32, 11, 1, 0, 16, 110336, 4, 1, 0, 0, 1, 1, 0},
+    {"perf c128 k3 d1 act-only", 128, 128, 128, 3, 1, 0, 16, 27584, 2, 0, 0, 0, 0, 1, 0},
+    {"perf c128 k7 d3 act-only", 128, 128, 128, 7, 3, 0, 16, 27584, 2, 0, 0, 0, 0, 1, 0},
+    {"perf c128 k7 d1 res f32+act", 128, 128, 128, 7, 1, 0, 16, 27584, 2, 1, 0, 0, 1, 1, 0},
 };
 static const int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 
@@ -270,6 +273,27 @@ int main(int argc, char** argv) {
   ms /= reps;
   const double flops = 2.0 * c.B * c.T * (double)c.n_total * c.taps * c.cin;
   printf("  time %.4f ms  -> %.1f TFLOP/s\n", ms, flops / ms * 1e-9);
+#ifdef E2E_TRACE
+  {
+    static unsigned long long tr[512][12];
+    launch_conv(plan, 0);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(tr, g_trace, sizeof(tr)));
+    const int nblk = plan.grid.x * plan.grid.y * plan.grid.z;
+    unsigned long long tmin = ~0ull;
+    for (int i = 0; i < 512 && i * 8 < nblk; ++i) tmin = tr[i][0] < tmin ? tr[i][0] : tmin;
+    printf("  trace (us rel. to first CTA start): blk sm | start setup slabTMA wDone | mmaW0 mmaP0 mmaIssued | accFull epiDone end\n");
+    for (int i = 0; i < 512 && i * 8 < nblk; ++i) {
+      if (!(i < 6 || i % 37 == 0)) continue;
+      printf("  %5d %3llu |", i * 8, tr[i][10]);
+      for (int s = 0; s < 10; ++s) {
+        printf(" %7.2f", (double)(tr[i][s] - tmin) * 1e-3);
+        if (s == 3 || s == 6) printf(" |");
+      }
+      printf("\n");
+    }
+  }
+#endif
   const bool ok = bad == 0 && bad2 == 0;
   printf("[cfg %d] %s\n", id, ok ? "PASS" : "FAIL");
   return ok ? 0 : 1;
