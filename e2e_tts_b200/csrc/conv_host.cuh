@@ -68,8 +68,9 @@ struct ConvPlan {
 };
 
 // Fill every geometry field of plan.p from the layer shape and the problem size.  `mt_pref` = preferred
-// number of 128-row tiles per CTA (reduced until TMEM and shared memory fit).
-inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pref) {
+// number of 128-row tiles per unit (1, 2 or 4; reduced until TMEM and shared memory fit); `n_sms` sizes the
+// persistent grid.
+inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pref, int n_sms = 148) {
   ConvParams& p = plan.p;
   if (s.cin != 32 && s.cin % 64 != 0) return fail(-2, "cin must be 32 or a multiple of 64");
   if (s.nt % 32 != 0 || s.nt > 256 || s.n_total % s.nt != 0) return fail(-2, "bad N tiling");
@@ -79,9 +80,10 @@ inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pr
   p.B = B;
   p.rowb = s.cin == 32 ? 64 : 128;
   p.panels = s.cin == 32 ? 1 : s.cin / 64;
-  if (p.panels > kMaxPanels) return fail(-2, "too many K panels");
+  if (p.panels > kMaxPanelSlots) return fail(-2, "too many K panels");
   p.nt = s.nt;
   p.n_total = s.n_total;
+  p.n_tiles = n_tiles;
   p.taps = s.taps;
   int smin = 0, smax = 0;
   for (int i = 0; i < n_tiles; ++i)
@@ -95,48 +97,73 @@ inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pr
   p.hl = -smin;
   const int tile_bytes = s.nt * p.rowb;
   const int total_tiles = p.panels * s.taps;
-  // ring stage ~ 32 KB (or the whole weight set when it is smaller)
+  // ring stage ~ 32 KB (one tile when a tile is that large): fewer barrier round trips for the MMA issuer
   int tpc = 32768 / tile_bytes;
   if (tpc < 1) tpc = 1;
   if (tpc > total_tiles) tpc = total_tiles;
   p.tiles_per_chunk = tpc;
   p.n_chunks = (total_tiles + tpc - 1) / tpc;
   p.stage_bytes = tpc * tile_bytes;
-  const int bar_bytes = 256;
-  for (int mt = mt_pref; mt >= 1; mt >>= 1) {
+  const int bar_bytes = 512;
+  const int budget = kSmemLimit - 1024 - bar_bytes;
+  int mt0 = mt_pref >= 4 ? 4 : (mt_pref >= 2 ? 2 : 1);
+  for (int mt = mt0; mt >= 1; mt >>= 1) {
     if (mt * s.nt > 512) continue;
     const int need = 128 * mt + p.hl + smax;
     for (int box = 128; box >= 16; box >>= 1) {
       const int rows = (need + box - 1) / box * box;
       if (rows - need > 32 && box > 16) continue;  // avoid large padding
-      const int slab = p.panels * rows * p.rowb;
-      int stages = (kSmemLimit - 1024 - bar_bytes - slab) / p.stage_bytes;
-      if (stages > p.n_chunks) stages = p.n_chunks;
-      if (stages > 4) stages = 4;
-      if (stages < (p.n_chunks > 1 ? 2 : 1)) continue;
-      p.mt = mt;
-      p.slab_rows = rows;
-      p.box_rows = box;
-      p.n_stages = stages;
-      int cols = 32;
-      while (cols < mt * s.nt) cols <<= 1;
-      p.tmem_cols = cols;
-      plan.smem_bytes = 1024 + slab + stages * p.stage_bytes + bar_bytes;
-      plan.grid = dim3((T + 128 * mt - 1) / (128 * mt), n_tiles, B);
-      return 0;
+      const int panel_bytes = rows * p.rowb;
+      int max_slots = 2 * p.panels < kMaxPanelSlots ? 2 * p.panels : kMaxPanelSlots;
+      for (int slots = max_slots; slots >= p.panels; --slots) {
+        int stages = (budget - slots * panel_bytes) / p.stage_bytes;
+        if (stages > 4) stages = 4;
+        const int want = slots > p.panels ? 3 : 2;  // extra panel slots must not starve the weight ring
+        if (stages < want) continue;
+        p.mt = mt;
+        p.slab_rows = rows;
+        p.box_rows = box;
+        p.panel_slots = slots;
+        p.n_stages = stages;
+        p.n_acc = 2 * mt * s.nt <= 512 ? 2 : 1;
+        p.tiles_per_b = (T + 128 * mt - 1) / (128 * mt);
+        p.n_units = B * p.tiles_per_b * n_tiles;
+        plan.smem_bytes = 1024 + slots * panel_bytes + stages * p.stage_bytes + bar_bytes;
+        plan.grid = dim3(p.n_units < n_sms ? p.n_units : n_sms, 1, 1);
+        return 0;
+      }
     }
   }
   return fail(-3, "convolution does not fit shared memory / TMEM");
 }
 
+typedef void (*ConvKernelFn)(const CUtensorMap, const ConvParams);
+
+inline ConvKernelFn conv_kernel_for(int rowb, int mt) {
+  if (rowb == 128) return mt == 4 ? conv_tc_kernel<128, 4> : (mt == 2 ? conv_tc_kernel<128, 2> : conv_tc_kernel<128, 1>);
+  return mt == 4 ? conv_tc_kernel<64, 4> : (mt == 2 ? conv_tc_kernel<64, 2> : conv_tc_kernel<64, 1>);
+}
+
+// Opt every instantiation into the 227 KB dynamic shared-memory limit (once per process and device).
+inline int conv_kernels_init() {
+  static int done_for_device = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (done_for_device == dev) return 0;
+  const int rowbs[2] = {128, 64}, mts[3] = {1, 2, 4};
+  for (int r : rowbs)
+    for (int m : mts) {
+      cudaError_t e = cudaFuncSetAttribute(conv_kernel_for(r, m), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+      if (e != cudaSuccess) return fail((int)e, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    }
+  done_for_device = dev;
+  return 0;
+}
+
 inline int launch_conv(const ConvPlan& plan, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-    if (e != cudaSuccess) return fail((int)e, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    attr_set = true;
-  }
-  conv_tc_kernel<<<plan.grid, kConvThreads, plan.smem_bytes, st>>>(plan.tm, plan.p);
+  int rc = conv_kernels_init();
+  if (rc) return rc;
+  conv_kernel_for(plan.p.rowb, plan.p.mt)<<<plan.grid, kConvThreads, plan.smem_bytes, st>>>(plan.tm, plan.p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("conv_tc launch: ") + cudaGetErrorString(e));
   return 0;

@@ -6,13 +6,23 @@
 //   * ConvTranspose1d(k=2u, stride=u, pad=u/2) (ups[i])      -> polyphase: N = u*C_out columns, every N-tile
 //                                                              uses two taps with shifts {0,-1} or {0,+1}
 // Data layout: activations are channels-last  [B][T][C]  bf16, so a tile of 128 consecutive time steps by 64
-// channels is a K-major UMMA A operand (time on M, channels on K).  One CTA loads ONE slab of
-// (128*mt + halo) rows per 64-channel panel with TMA (out-of-range rows are zero-filled by the TMA unit =
-// Conv1d's per-layer zero padding) and serves every tap from that slab by offsetting the UMMA descriptor's
-// start address by `shift` rows.  Weights are pre-packed on the host as ready-to-use swizzled smem images
-// [n_tile][panel][tap][nt rows][row bytes] and streamed through an mbarrier ring with 1-D bulk copies.
-// Accumulators (mt tiles of 128 x nt fp32) live in TMEM; four epilogue warps read them back with
-// tcgen05.ld and fuse bias, residual add, the 3-way resblock sum / 3, LeakyReLU and the bf16 cast.
+// channels is a K-major UMMA A operand (time on M, channels on K).  A work unit is (utterance, tile of 128*MT
+// time steps, N tile).  For every unit ONE slab of (128*MT + halo) rows per 64-channel panel is brought in by
+// TMA (out-of-range rows are zero-filled by the TMA unit = Conv1d's per-layer zero padding) and serves every
+// tap by offsetting the UMMA descriptor's start address by `shift` rows.  Weights are pre-packed on the host
+// as ready-to-use swizzled smem images [n_tile][panel][tap][nt rows][row bytes] and streamed with 1-D bulk
+// copies.
+//
+// The kernel is persistent (one CTA per SM, units strided over CTAs) and warp-specialised:
+//   warp 0   panel producer : TMA slab loads into a ring of panel buffers (runs ahead across units)
+//   warp 1   weight producer: bulk copies into the weight ring
+//   warp 2   MMA issuer     : one thread issues tcgen05.mma; the (M tile, K step) loops are unrolled and the
+//                             descriptors are advanced by adding to their low word only
+//   warp 3   TMEM allocator
+//   warps 4-11 epilogue     : tcgen05.ld the fp32 accumulators (two warps per TMEM lane quarter), fuse bias,
+//                             residual add (prefetched while the MMAs run), resblock sum, /3, LeakyReLU, casts
+// Accumulators are double-buffered in TMEM when 2*MT*nt <= 512 columns, so the epilogue of unit i overlaps
+// the MMAs of unit i+1.
 #pragma once
 #include "ptx.cuh"
 
@@ -20,103 +30,111 @@ namespace e2e {
 
 constexpr int kMaxTaps = 16;
 constexpr int kMaxNTiles = 16;
-constexpr int kMaxPanels = 8;
+constexpr int kMaxPanelSlots = 8;
 constexpr int kMaxStages = 8;
-constexpr int kConvThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kConvThreads = 384;
+constexpr int kEpiWarps = 8;
 
 struct ConvParams {
   int T;                // time steps per utterance (rows); input and output have the same row count
   int B;                // utterances
   int panels;           // K panels (64 channels each, or one 32-channel panel)
   int rowb;             // bytes per panel row: 128 (64 ch, SWIZZLE_128B) or 64 (32 ch, SWIZZLE_64B)
-  int nt;               // output columns per CTA (UMMA N), multiple of 16, <= 256
+  int nt;               // output columns per unit (UMMA N), multiple of 32, <= 256
   int n_total;          // total output columns (row stride of the outputs)
-  int mt;               // 128-row M tiles per CTA (mt*nt <= 512 TMEM columns)
+  int n_tiles;          // n_total / nt
+  int mt;               // 128-row M tiles per unit (== template MT)
   int taps;             // taps per N tile
   int hl;               // rows of left halo in the slab  (= max(0, -min shift))
   int slab_rows;        // rows per panel in shared memory (multiple of box_rows)
   int box_rows;         // TMA box height
+  int panel_slots;      // panel buffers in the ring (>= panels)
   int tiles_per_chunk;  // weight tiles (one tap of one panel) per ring stage
-  int n_chunks;         // ring transactions per CTA
+  int n_chunks;         // ring transactions per unit
   int n_stages;         // ring depth
   int stage_bytes;      // bytes per ring stage (multiple of 1024)
-  int tmem_cols;        // power of two >= max(32, mt*nt)
+  int n_acc;            // TMEM accumulator sets (1 or 2)
+  int tiles_per_b;      // time tiles per utterance
+  int n_units;          // B * tiles_per_b * n_tiles
   float divisor;        // epilogue: 0 = none, else out /= divisor (generator.py:48, xs / num_kernels)
   float slope;          // LeakyReLU slope applied to out_act
   int8_t shift[kMaxNTiles][kMaxTaps];  // row shift of each tap, per N tile
   const uint8_t* w;     // packed weights
   const float* bias;    // [n_total]
-  const float* res_in;  // fp32 [B][T][n_total] residual (x of `xt + x`, layers.py:39) or nullptr
+  const __nv_bfloat16* res_act;  // bf16 [B][T][n_total] = leaky_relu(x, 1/res_inv_slope) of the residual x of
+                                 // `xt + x` (layers.py:39), or nullptr; x is recovered by the inverse LeakyReLU
+  float res_inv_slope;  // 1 / slope used when res_act was written (10 for LRELU_SLOPE = 0.1)
   const float* sum_in;  // fp32 running sum over resblocks (generator.py:44-47) or nullptr
   float* out_f32;       // fp32 [B][T][n_total] or nullptr
   __nv_bfloat16* out_act;  // bf16 [B][T][n_total] = leaky_relu(out, slope) or nullptr
 };
 
 #ifdef E2E_TRACE
-// Debug build only: per-CTA phase timestamps (globaltimer ns) for every 8th CTA, read back by tests/cuda.
+// Debug build only: per-CTA phase timestamps (globaltimer ns), read back by tests/cuda.
 __device__ unsigned long long g_trace[512][12];
 __device__ __forceinline__ unsigned long long gtime_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-#define E2E_TR(slot)                                               \
-  do {                                                             \
-    if (trace_id >= 0) g_trace[trace_id][slot] = gtime_ns();       \
+#define E2E_TR(slot)                                                     \
+  do {                                                                   \
+    if (blockIdx.x < 512) g_trace[blockIdx.x][slot] = gtime_ns();        \
   } while (0)
 #else
 #define E2E_TR(slot)
 #endif
 
+template <int ROWB, int MT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
+  constexpr int KS = ROWB / 32;          // UMMA K steps (16 bf16 = 32 B) per panel row
+  constexpr uint32_t ROW16 = ROWB >> 4;  // row pitch in descriptor address units (16 B)
+  // high word of the K-major swizzled smem descriptor: SBO = 8 rows, version 1, layout 128B / 64B
+  constexpr uint32_t DESC_HI = ((8u * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
+
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int rowb = p.rowb;
-  const int panel_bytes = p.slab_rows * rowb;
-  const int tile_bytes = p.nt * rowb;
+  const int panel_bytes = p.slab_rows * ROWB;
+  const int tile_bytes = p.nt * ROWB;
   const int total_tiles = p.panels * p.taps;
 
-  uint8_t* slab = smem;
-  uint8_t* ring = slab + p.panels * panel_bytes;
+  uint8_t* slabs = smem;
+  uint8_t* ring = slabs + p.panel_slots * panel_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.n_stages * p.stage_bytes);
-  uint64_t* panel_full = bars;                      // [kMaxPanels]
-  uint64_t* ring_full = bars + kMaxPanels;          // [kMaxStages]
-  uint64_t* ring_empty = ring_full + kMaxStages;    // [kMaxStages]
-  uint64_t* acc_full = ring_empty + kMaxStages;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* panel_full = bars;                          // [kMaxPanelSlots]
+  uint64_t* panel_empty = panel_full + kMaxPanelSlots;  // [kMaxPanelSlots]
+  uint64_t* w_full = panel_empty + kMaxPanelSlots;      // [kMaxStages]
+  uint64_t* w_empty = w_full + kMaxStages;              // [kMaxStages]
+  uint64_t* acc_full = w_empty + kMaxStages;            // [2]
+  uint64_t* acc_empty = acc_full + 2;                   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int t0 = blockIdx.x * (128 * p.mt);
-  const int nti = blockIdx.y;
-  const int b = blockIdx.z;
-#ifdef E2E_TRACE
-  const int lin_ = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-  const int trace_id = (lin_ % 8 == 0 && lin_ / 8 < 512) ? lin_ / 8 : -1;
   if (threadIdx.x == 0) {
     E2E_TR(0);
-    if (trace_id >= 0) {
-      unsigned int smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      g_trace[trace_id][10] = smid;
-    }
-  }
+#ifdef E2E_TRACE
+    if (blockIdx.x < 512) g_trace[blockIdx.x][8] = g_trace[blockIdx.x][9] = 0;
 #endif
-
-  if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_in);
-    for (int i = 0; i < p.panels; ++i) mbar_init(&panel_full[i], 1);
-    for (int i = 0; i < p.n_stages; ++i) {
-      mbar_init(&ring_full[i], 1);
-      mbar_init(&ring_empty[i], 1);
+    for (int i = 0; i < p.panel_slots; ++i) {
+      mbar_init(&panel_full[i], 1);
+      mbar_init(&panel_empty[i], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kEpiWarps);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == 3) {
+    tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
   tc_fence_before_sync();
@@ -127,109 +145,197 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- TMA producer ----------------
-      const int ch_per_panel = rowb / 2;
+      // ---------------- panel producer (TMA) ----------------
+      constexpr int ch_per_panel = ROWB / 2;
       const int boxes = p.slab_rows / p.box_rows;
-      for (int pn = 0; pn < p.panels; ++pn) {
-        mbar_arrive_expect_tx(&panel_full[pn], panel_bytes);
-        for (int bx = 0; bx < boxes; ++bx)
-          tma_load_3d(slab + pn * panel_bytes + bx * p.box_rows * rowb, &tm_in, pn * ch_per_panel,
-                      t0 - p.hl + bx * p.box_rows, b, &panel_full[pn]);
+      uint32_t slot = 0, par = 1;  // ring position; `par` is the parity a fresh/recycled slot is waited on
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int tb = u / p.n_tiles;
+        const int b = tb / p.tiles_per_b;
+        const int t0 = (tb - b * p.tiles_per_b) * (128 * MT);
+        for (int pn = 0; pn < p.panels; ++pn) {
+          mbar_wait(&panel_empty[slot], par, 0x100 + slot);
+          mbar_arrive_expect_tx(&panel_full[slot], panel_bytes);
+          uint8_t* dst = slabs + slot * panel_bytes;
+          for (int bx = 0; bx < boxes; ++bx)
+            tma_load_3d(dst + bx * p.box_rows * ROWB, &tm_in, pn * ch_per_panel, t0 - p.hl + bx * p.box_rows, b,
+                        &panel_full[slot]);
+          if (++slot == (uint32_t)p.panel_slots) {
+            slot = 0;
+            par ^= 1;
+          }
+        }
       }
-      E2E_TR(2);
-      const uint8_t* wsrc = p.w + static_cast<size_t>(nti) * total_tiles * tile_bytes;
-      for (int c = 0; c < p.n_chunks; ++c) {
-        const int stage = c % p.n_stages;
-        const uint32_t par = (c / p.n_stages) & 1;
-        mbar_wait(&ring_empty[stage], par ^ 1, 0x100 + stage);
-        const int first = c * p.tiles_per_chunk;
-        const int ntile = min(p.tiles_per_chunk, total_tiles - first);
-        const uint32_t bytes = ntile * tile_bytes;
-        mbar_arrive_expect_tx(&ring_full[stage], bytes);
-        bulk_load_1d(ring + stage * p.stage_bytes, wsrc + static_cast<size_t>(first) * tile_bytes, bytes,
-                     &ring_full[stage]);
-      }
-      E2E_TR(3);
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // ---------------- MMA issuer ----------------
-      const uint32_t idesc = umma_idesc_bf16(128, p.nt);
-      const uint32_t slab_addr = smem_u32(slab);
-      const uint32_t ring_addr = smem_u32(ring);
-      const int ksteps = rowb / 32;
-      int tile = 0;
-      for (int c = 0; c < p.n_chunks; ++c) {
-        const int stage = c % p.n_stages;
-        const uint32_t par = (c / p.n_stages) & 1;
-        mbar_wait(&ring_full[stage], par, 0x200 + stage);
-        tc_fence_after_sync();
-        if (c == 0) E2E_TR(4);
-        const int ntile = min(p.tiles_per_chunk, total_tiles - c * p.tiles_per_chunk);
-        for (int i = 0; i < ntile; ++i, ++tile) {
-          const int pn = tile / p.taps;
-          const int tap = tile - pn * p.taps;
-          if (tap == 0) {
-            mbar_wait(&panel_full[pn], 0, 0x300 + pn);
-            tc_fence_after_sync();
-            if (pn == 0) E2E_TR(5);
+      // ---------------- weight producer (bulk copies) ----------------
+      uint32_t stage = 0, par = 1;
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+        const int nti = u % p.n_tiles;
+        const uint8_t* wsrc = p.w + static_cast<size_t>(nti) * total_tiles * tile_bytes;
+        int first = 0;
+        for (int c = 0; c < p.n_chunks; ++c, first += p.tiles_per_chunk) {
+          mbar_wait(&w_empty[stage], par, 0x200 + stage);
+          const int ntile = min(p.tiles_per_chunk, total_tiles - first);
+          const uint32_t bytes = ntile * tile_bytes;
+          mbar_arrive_expect_tx(&w_full[stage], bytes);
+          bulk_load_1d(ring + stage * p.stage_bytes, wsrc + static_cast<size_t>(first) * tile_bytes, bytes,
+                       &w_full[stage]);
+          if (++stage == (uint32_t)p.n_stages) {
+            stage = 0;
+            par ^= 1;
           }
-          const int row0 = p.hl + p.shift[nti][tap];
-          const uint32_t a_base = slab_addr + pn * panel_bytes + row0 * rowb;
-          const uint32_t b_base = ring_addr + stage * p.stage_bytes + i * tile_bytes;
-          for (int m = 0; m < p.mt; ++m) {
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint32_t a_addr = a_base + m * 128 * rowb + ks * 32;
-              const uint64_t da = umma_smem_desc(a_addr, rowb, 0);
-              const uint64_t db = umma_smem_desc(b_base + ks * 32, rowb, 0);
-              umma_bf16(tmem_base + m * p.nt, da, db, idesc, (tile | ks) != 0 ? 1u : 0u);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------- MMA issuer ----------------
+    // The whole warp runs the loop (warp-uniform control flow and address arithmetic); one elected lane issues
+    // the tcgen05 instructions.  No divisions: ring positions are counters that wrap.
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(128, p.nt);
+    const uint32_t slab_lo = ((smem_u32(slabs) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t panel16 = panel_bytes >> 4, stage16 = p.stage_bytes >> 4, tile16 = tile_bytes >> 4;
+    uint32_t slot = 0, ppar = 0, stage = 0, wpar = 0, acc = 0, apar = 1;
+    bool first_unit = true;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int nti = u % p.n_tiles;
+      mbar_wait(&acc_empty[acc], apar, 0x300 + acc);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * (MT * p.nt);
+      if (first_unit && leader) E2E_TR(2);
+      int tap = 0, left = total_tiles;
+      uint32_t accum = 0;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        mbar_wait(&w_full[stage], wpar, 0x400 + stage);
+        tc_fence_after_sync();
+        const int ntile = min(p.tiles_per_chunk, left);
+        left -= ntile;
+        uint32_t b_lo = ring_lo + stage * stage16;
+        for (int i = 0; i < ntile; ++i, b_lo += tile16) {
+          if (tap == 0) {
+            mbar_wait(&panel_full[slot], ppar, 0x500 + slot);
+            tc_fence_after_sync();
+          }
+          const uint32_t a_lo = slab_lo + slot * panel16 + (p.hl + p.shift[nti][tap]) * ROW16;
+          if (leader) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                const uint64_t da = (static_cast<uint64_t>(DESC_HI) << 32) | (a_lo + m * (128 * ROW16) + ks * 2);
+                const uint64_t db = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + ks * 2);
+                if (ks == 0)
+                  umma_bf16(d_tmem + m * p.nt, da, db, idesc, accum);
+                else
+                  umma_bf16_acc(d_tmem + m * p.nt, da, db, idesc);
+              }
+            }
+          }
+          accum = 1;
+          if (++tap == p.taps) {
+            if (leader) umma_commit(&panel_empty[slot]);  // slab panel consumed: the producer may refill it
+            tap = 0;
+            if (++slot == (uint32_t)p.panel_slots) {
+              slot = 0;
+              ppar ^= 1;
             }
           }
         }
-        umma_commit(&ring_empty[stage]);  // frees the weight stage once these MMAs have read it
+        if (leader) umma_commit(&w_empty[stage]);
+        if (++stage == (uint32_t)p.n_stages) {
+          stage = 0;
+          wpar ^= 1;
+        }
       }
-      E2E_TR(6);
-      umma_commit(acc_full);
+      if (leader) umma_commit(&acc_full[acc]);
+      if (first_unit && leader) E2E_TR(3);
+      first_unit = false;
+      if (++acc == (uint32_t)p.n_acc) {
+        acc = 0;
+        apar ^= 1;
+      }
     }
-  } else {
+    if (leader) E2E_TR(4);
+  } else if (warp >= 4) {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
-    const int quarter = warp & 3;  // TMEM lanes 32*quarter .. +31 are the ones this warp may read
-    mbar_wait(acc_full, 0, 0x400);
-    tc_fence_after_sync();
-    if (threadIdx.x == 64) E2E_TR(7);
-    const int nchunk = p.nt / 32;
-    for (int m = 0; m < p.mt; ++m) {
-      const int t = t0 + m * 128 + quarter * 32 + lane;
-      const bool valid = t < p.T;
-      const size_t row_off = (static_cast<size_t>(b) * p.T + (valid ? t : 0)) * p.n_total + nti * p.nt;
-      for (int cc = 0; cc < nchunk; ++cc) {
+    const int e = warp - 4;
+    const int quarter = e & 3;  // == warp % 4: the TMEM lanes this warp may read
+    const int half = e >> 2;
+    const int nchunk = p.nt >> 5;
+    const int items = MT * nchunk;  // (m tile, 32-column chunk) pairs; this warp takes items with item%2 == half
+    uint32_t it = 0, acc = 0, apar = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
+      const int nti = u % p.n_tiles;
+      const int tb = u / p.n_tiles;
+      const int b = tb / p.tiles_per_b;
+      const int t0 = (tb - b * p.tiles_per_b) * (128 * MT);
+      const uint32_t d_tmem = tmem_base + acc * (MT * p.nt) + (static_cast<uint32_t>(quarter * 32) << 16);
+      const int row_in_tile = quarter * 32 + lane;
+
+      // Residual: 32 bf16 of this thread's row per item, prefetched two items ahead (loads of item i+2 are in
+      // flight while item i is processed), so the L2/HBM latency is off the critical path.
+      uint4 rqa[4], rqb[4];
+      auto prefetch = [&](int item, uint4 (&dst)[4]) {
+        const int m = item / nchunk, cc = item - m * nchunk;
+        const int t = t0 + m * 128 + row_in_tile;
+        if (p.res_act && item < items && t < p.T) {
+          const uint4* src = reinterpret_cast<const uint4*>(
+              p.res_act + (static_cast<size_t>(b) * p.T + t) * p.n_total + nti * p.nt + cc * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = src[i];  // plain loads: the buffer may be updated in place
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      prefetch(half, rqa);      // overlaps the MMAs of this unit
+      prefetch(half + 2, rqb);
+      mbar_wait(&acc_full[acc], apar, 0x600 + acc);
+      tc_fence_after_sync();
+      if (it == 0 && threadIdx.x == 128) E2E_TR(5);
+
+      auto process = [&](int item, uint4 (&rq)[4]) {
+        const int m = item / nchunk, cc = item - m * nchunk;
+        const int t = t0 + m * 128 + row_in_tile;
+        const bool valid = t < p.T;
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + m * p.nt + cc * 32, v);
+        tmem_ld_32x32(d_tmem + m * p.nt + cc * 32, v);
         tmem_ld_wait();
+        float f[32];
+        const int n0 = nti * p.nt + cc * 32;
+        const float inv = p.res_inv_slope;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t w4[4] = {rq[i].x, rq[i].y, rq[i].z, rq[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            // bf16 -> fp32 is a 16-bit shift; x = a > 0 ? a : a / slope
+            float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
+            lo = lo > 0.f ? lo : lo * inv;
+            hi = hi > 0.f ? hi : hi * inv;
+            f[8 * i + 2 * j] = lo;
+            f[8 * i + 2 * j + 1] = hi;
+          }
+        }
+        prefetch(item + 4, rq);  // refill this slot for the item after next
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+          f[4 * i] += __uint_as_float(v[4 * i]) + bv.x;
+          f[4 * i + 1] += __uint_as_float(v[4 * i + 1]) + bv.y;
+          f[4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bv.z;
+          f[4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bv.w;
+        }
         if (valid) {
-          const int n0 = nti * p.nt + cc * 32;
-          const size_t off = row_off + cc * 32;
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 bv = *reinterpret_cast<const float4*>(p.bias + n0 + i);
-            f[i] = __uint_as_float(v[i]) + bv.x;
-            f[i + 1] = __uint_as_float(v[i + 1]) + bv.y;
-            f[i + 2] = __uint_as_float(v[i + 2]) + bv.z;
-            f[i + 3] = __uint_as_float(v[i + 3]) + bv.w;
-          }
-          if (p.res_in) {
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 r = *reinterpret_cast<const float4*>(p.res_in + off + i);
-              f[i] += r.x; f[i + 1] += r.y; f[i + 2] += r.z; f[i + 3] += r.w;
-            }
-          }
+          const size_t off = (static_cast<size_t>(b) * p.T + t) * p.n_total + n0;
           if (p.sum_in) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              const float4 r = *reinterpret_cast<const float4*>(p.sum_in + off + i);
-              f[i] += r.x; f[i + 1] += r.y; f[i + 2] += r.z; f[i + 3] += r.w;
+            for (int i = 0; i < 8; ++i) {
+              const float4 s = __ldg(reinterpret_cast<const float4*>(p.sum_in + off) + i);
+              f[4 * i] += s.x; f[4 * i + 1] += s.y; f[4 * i + 2] += s.z; f[4 * i + 3] += s.w;
             }
           }
           if (p.divisor != 0.f) {
@@ -239,38 +345,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
           }
           if (p.out_f32) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4)
-              *reinterpret_cast<float4*>(p.out_f32 + off + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(p.out_f32 + off)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           }
           if (p.out_act) {
             const float s = p.slope;
 #pragma unroll
-            for (int i = 0; i < 32; i += 8) {
+            for (int i = 0; i < 4; ++i) {
               uint32_t pk[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                float a = f[i + 2 * j], c = f[i + 2 * j + 1];
+                float a = f[8 * i + 2 * j], c = f[8 * i + 2 * j + 1];
                 a = a > 0.f ? a : a * s;
                 c = c > 0.f ? c : c * s;
                 __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
                 pk[j] = *reinterpret_cast<uint32_t*>(&h);
               }
-              *reinterpret_cast<uint4*>(p.out_act + off + i) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              reinterpret_cast<uint4*>(p.out_act + off)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           }
         }
+      };
+      for (int item = half; item < items; item += 4) {
+        process(item, rqa);
+        if (item + 2 < items) process(item + 2, rqb);
+      }
+      // all of this warp's TMEM reads of the unit are complete (tcgen05.wait::ld above): release the accumulator
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (it == 0 && threadIdx.x == 128) E2E_TR(6);
+      if (++acc == (uint32_t)p.n_acc) {
+        acc = 0;
+        apar ^= 1;
       }
     }
   }
 
-  if (threadIdx.x == 64) E2E_TR(8);
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 3) {
     __syncwarp();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    tmem_dealloc(tmem_base, 512);
   }
-  if (threadIdx.x == 0) E2E_TR(9);
+  if (threadIdx.x == 0) E2E_TR(7);
 }
 
 }  // namespace e2e

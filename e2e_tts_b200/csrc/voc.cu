@@ -44,9 +44,11 @@ struct PlanKey {
   }
 };
 
+// Activations live in HBM ONCE, as bf16 leaky_relu(x): that tensor is both the next convolution's operand and
+// (through the inverse LeakyReLU) the residual x of `xt + x`.  Only the running resblock sum is fp32.
 struct Buffers {
   __nv_bfloat16 *melA, *preA, *A0, *A1, *M, *Y;
-  float *X0, *X1, *SUM;
+  float* SUM;
   size_t total;
 };
 
@@ -180,6 +182,9 @@ extern "C" int e2e_voc_create(const e2e_voc_config* cfg, e2e_voc** out) {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return fail((int)e, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
   cudaDeviceGetAttribute(&v->n_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (v->n_sms < 1) v->n_sms = 148;
+  int rc_init = conv_kernels_init();
+  if (rc_init) return rc_init;
   *out = v.release();
   return 0;
 }
@@ -301,8 +306,6 @@ static void carve(const e2e_voc* v, int B, int T, void* ws, Buffers& b) {
   b.A1 = (__nv_bfloat16*)take(E * 2);
   b.M = (__nv_bfloat16*)take(E * 2);
   b.Y = (__nv_bfloat16*)take(E * 2);
-  b.X0 = (float*)take(E * 4);
-  b.X1 = (float*)take(E * 4);
   b.SUM = (float*)take(E * 4);
   b.total = off;
 }
@@ -316,26 +319,38 @@ extern "C" size_t e2e_voc_workspace_bytes(const e2e_voc* v, int32_t B, int32_t T
 
 // One conv launch: input activation `in` ([B][T][cin] bf16), outputs as requested.
 static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int T, const __nv_bfloat16* in,
-                        const float* res_in, const float* sum_in, float* out_f32, __nv_bfloat16* out_act,
+                        const __nv_bfloat16* res_act, const float* sum_in, float* out_f32, __nv_bfloat16* out_act,
                         float slope, float divisor) {
   Layer& L = v->layers[layer];
   Op op;
   op.kind = 1;
   op.layer = layer;
   const ConvShape& s = L.shape;
-  int mt = 512 / s.nt;
-  if (mt > 4) mt = 4;
+  // Units per CTA of the persistent grid are quantised: pick the tile height (128*mt rows) with the best
+  // balance, preferring taller tiles (fewer weight re-streams per row) when the balance is within 6 %.
   const int n_tiles = s.n_total / s.nt;
-  // keep at least ~2 waves of CTAs when the problem allows it
-  while (mt > 1 && (long long)((T + 128 * mt - 1) / (128 * mt)) * n_tiles * B < 2LL * v->n_sms) mt >>= 1;
-  int rc = plan_conv(op.plan, s, B, T, mt);
+  int mt = 1;
+  double best = 0.0;
+  for (int cand = 1; cand <= 4; cand <<= 1) {
+    if (cand * s.nt > 512) break;
+    const long long units = (long long)((T + 128 * cand - 1) / (128 * cand)) * n_tiles * B;
+    const long long rounds = (units + v->n_sms - 1) / v->n_sms;
+    // useful rows / rows the busiest CTA pays for
+    const double eff = (double)T * B * n_tiles / ((double)rounds * v->n_sms * 128.0 * cand);
+    if (eff >= best * 0.94) {
+      if (eff > best) best = eff;
+      mt = cand;
+    }
+  }
+  int rc = plan_conv(op.plan, s, B, T, mt, v->n_sms);
   if (rc) return rc;
   ConvParams& p = op.plan.p;
   rc = make_act_tensor_map(&op.plan.tm, in, B, T, s.cin, p.rowb / 2, p.box_rows);
   if (rc) return rc;
   p.w = L.d_w;
   p.bias = L.d_bias;
-  p.res_in = res_in;
+  p.res_act = res_act;
+  p.res_inv_slope = 10.0f;  // 1 / LRELU_SLOPE: every residual tensor was written with slope 0.1
   p.sum_in = sum_in;
   p.out_f32 = out_f32;
   p.out_act = out_act;
@@ -362,8 +377,8 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
   const __nv_bfloat16* stage_in = bf.preA;
   int Ts = T;
   for (int i = 0; i < c.num_upsamples; ++i) {
-    // x = ups[i](leaky_relu(x)) : writes the residual stream X0 (fp32) and its activation A0 (bf16)
-    rc = make_conv_op(v, ops, v->by_name["ups." + std::to_string(i)], B, Ts, stage_in, nullptr, nullptr, bf.X0,
+    // x = ups[i](leaky_relu(x)) : writes A0 = bf16 leaky_relu(x, 0.1), the stage's shared input
+    rc = make_conv_op(v, ops, v->by_name["ups." + std::to_string(i)], B, Ts, stage_in, nullptr, nullptr, nullptr,
                       bf.A0, kSlope, 0.f);
     if (rc) return rc;
     Ts *= c.upsample_rates[i];
@@ -373,12 +388,11 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
     for (int j = 0; j < c.num_kernels; ++j) {
       const std::string base = "resblocks." + std::to_string(i * c.num_kernels + j);
       const int nd = c.num_dilations[j];
-      const float* xin = bf.X0;
       const __nv_bfloat16* ain = bf.A0;
       for (int m = 0; m < nd; ++m) {
         const bool last = m + 1 == nd;
         // where does x_new = conv(...) + x go?
-        float* of32 = bf.X1;
+        float* of32 = nullptr;
         __nv_bfloat16* oact = bf.A1;
         const float* sum_in = nullptr;
         float divisor = 0.f, slope = kSlope;
@@ -397,15 +411,14 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
           rc = make_conv_op(v, ops, v->by_name[base + ".convs1." + std::to_string(m)], B, Ts, ain, nullptr, nullptr,
                             nullptr, bf.M, kSlope, 0.f);
           if (rc) return rc;
-          rc = make_conv_op(v, ops, v->by_name[base + ".convs2." + std::to_string(m)], B, Ts, bf.M, xin, sum_in,
+          rc = make_conv_op(v, ops, v->by_name[base + ".convs2." + std::to_string(m)], B, Ts, bf.M, ain, sum_in,
                             of32, oact, slope, divisor);
           if (rc) return rc;
         } else {
-          rc = make_conv_op(v, ops, v->by_name[base + ".convs." + std::to_string(m)], B, Ts, ain, xin, sum_in, of32,
+          rc = make_conv_op(v, ops, v->by_name[base + ".convs." + std::to_string(m)], B, Ts, ain, ain, sum_in, of32,
                             oact, slope, divisor);
           if (rc) return rc;
         }
-        xin = bf.X1;
         ain = bf.A1;
       }
     }

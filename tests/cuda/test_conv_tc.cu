@@ -63,7 +63,7 @@ static const Cfg kCfgs[] = {
 };
 static const int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 
-__global__ void ref_conv(const __nv_bfloat16* x, const float* wg, const float* bias, const float* res,
+__global__ void ref_conv(const __nv_bfloat16* x, const float* wg, const float* bias, const __nv_bfloat16* res,
                          const float* sum, float* out, int B, int T, int cin, int n_total, int nt, int taps,
                          const int* shifts, int div3) {
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
@@ -82,7 +82,10 @@ __global__ void ref_conv(const __nv_bfloat16* x, const float* wg, const float* b
     for (int c = 0; c < cin; ++c) acc += __bfloat162float(xr[c]) * wr[c];
   }
   float v = acc + bias[n];
-  if (res) v += res[idx];
+  if (res) {
+    const float a = __bfloat162float(res[idx]);
+    v += a > 0.f ? a : a * 10.0f;
+  }
   if (sum) v += sum[idx];
   if (div3) v = v / 3.0f;
   out[idx] = v;
@@ -137,13 +140,14 @@ int main(int argc, char** argv) {
                no = (size_t)c.B * c.T * c.n_total;
   std::vector<uint16_t> hx(nx);
   for (auto& v : hx) v = f32_to_bf16_rn(nd(rng));
-  std::vector<float> hw(nw), hb(c.n_total), hres, hsum;
+  std::vector<float> hw(nw), hb(c.n_total), hsum;
+  std::vector<uint16_t> hres;
   const float wscale = 1.0f / sqrtf((float)c.cin * c.taps);
   for (auto& v : hw) v = bf16_to_f32(f32_to_bf16_rn(nd(rng) * wscale));
   for (auto& v : hb) v = nd(rng) * 0.1f;
   if (c.res) {
     hres.resize(no);
-    for (auto& v : hres) v = nd(rng);
+    for (auto& v : hres) v = f32_to_bf16_rn(nd(rng));
   }
   if (c.sum) {
     hsum.resize(no);
@@ -153,7 +157,8 @@ int main(int argc, char** argv) {
   pack_conv_weights(s, hw.data(), hpack.data());
 
   __nv_bfloat16 *dx, *dact = nullptr;
-  float *dw, *db, *dres = nullptr, *dsum = nullptr, *dout = nullptr, *dref;
+  float *dw, *db, *dsum = nullptr, *dout = nullptr, *dref;
+  __nv_bfloat16* dres = nullptr;
   uint8_t* dpack;
   int* dshift;
   CK(cudaMalloc(&dx, nx * 2));
@@ -168,8 +173,8 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dpack, hpack.data(), hpack.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dshift, s.shifts.data(), s.shifts.size() * 4, cudaMemcpyHostToDevice));
   if (c.res) {
-    CK(cudaMalloc(&dres, no * 4));
-    CK(cudaMemcpy(dres, hres.data(), no * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&dres, no * 2));
+    CK(cudaMemcpy(dres, hres.data(), no * 2, cudaMemcpyHostToDevice));
   }
   if (c.sum) {
     CK(cudaMalloc(&dsum, no * 4));
@@ -198,15 +203,16 @@ int main(int argc, char** argv) {
   }
   p.w = dpack;
   p.bias = db;
-  p.res_in = dres;
+  p.res_act = dres;
+  p.res_inv_slope = 10.0f;
   p.sum_in = dsum;
   p.out_f32 = dout;
   p.out_act = dact;
   p.slope = 0.1f;
   p.divisor = c.div3 ? 3.0f : 0.f;
-  printf("  plan: grid=(%d,%d,%d) smem=%d mt=%d slab_rows=%d box=%d stages=%d stage_bytes=%d chunks=%d tmem=%d hl=%d\n",
-         plan.grid.x, plan.grid.y, plan.grid.z, plan.smem_bytes, p.mt, p.slab_rows, p.box_rows, p.n_stages,
-         p.stage_bytes, p.n_chunks, p.tmem_cols, p.hl);
+  printf("  plan: grid=%d units=%d smem=%d mt=%d slab_rows=%d box=%d panel_slots=%d stages=%d stage_bytes=%d chunks=%d n_acc=%d hl=%d\n",
+         plan.grid.x, p.n_units, plan.smem_bytes, p.mt, p.slab_rows, p.box_rows, p.panel_slots, p.n_stages,
+         p.stage_bytes, p.n_chunks, p.n_acc, p.hl);
 
   rc = launch_conv(plan, 0);
   if (rc) {
@@ -279,18 +285,18 @@ int main(int argc, char** argv) {
     launch_conv(plan, 0);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpyFromSymbol(tr, g_trace, sizeof(tr)));
-    const int nblk = plan.grid.x * plan.grid.y * plan.grid.z;
+    const int nblk = plan.grid.x;
     unsigned long long tmin = ~0ull;
-    for (int i = 0; i < 512 && i * 8 < nblk; ++i) tmin = tr[i][0] < tmin ? tr[i][0] : tmin;
-    printf("  trace (us rel. to first CTA start): blk sm | start setup slabTMA wDone | mmaW0 mmaP0 mmaIssued | accFull epiDone end\n");
-    for (int i = 0; i < 512 && i * 8 < nblk; ++i) {
-      if (!(i < 6 || i % 37 == 0)) continue;
-      printf("  %5d %3llu |", i * 8, tr[i][10]);
-      for (int s = 0; s < 10; ++s) {
+    for (int i = 0; i < 512 && i < nblk; ++i) tmin = tr[i][0] < tmin ? tr[i][0] : tmin;
+    printf("  trace (us rel. to first CTA start): cta | start setup | mma0begin mma0issued mmaAllIssued | epi0accFull epi0done | end\n");
+    for (int i = 0; i < 512 && i < nblk; ++i) {
+      if (!(i < 4 || i % 49 == 0)) continue;
+      printf("  %5d |", i);
+      for (int s = 0; s < 8; ++s) {
         printf(" %7.2f", (double)(tr[i][s] - tmin) * 1e-3);
-        if (s == 3 || s == 6) printf(" |");
+        if (s == 1 || s == 4 || s == 6) printf(" |");
       }
-      printf("\n");
+      printf(" | unit0 waits: weights %.2f panels %.2f us\n", tr[i][8] * 1e-3, tr[i][9] * 1e-3);
     }
   }
 #endif
