@@ -1,0 +1,418 @@
+// Fused residual pair of ResBlock1 (reference e2e_tts/models/vocoder/layers.py:34-39):
+//
+//     xt = c1(leaky_relu(x))          dilated conv, k taps, dilation d
+//     xt = c2(leaky_relu(xt))         conv, k taps, dilation 1
+//     x  = xt + x
+//
+// in ONE persistent tcgen05 kernel.  leaky_relu(x) arrives as a bf16 channels-last slab by TMA (rows outside the
+// utterance zero-filled = c1's zero padding); c1's accumulators are read from TMEM, biased, activated, rounded to
+// bf16 and written into a swizzled shared-memory slab `M` that is directly c2's UMMA A operand (rows outside
+// [0,T) forced to zero = c2's zero padding, SURVEY.md §8 a'1) — the intermediate never touches HBM.  c2's epilogue
+// adds the residual (recovered from the stored bf16 leaky_relu(x) by the inverse LeakyReLU), the running resblock
+// sum and the /3, and writes the next activation.
+//
+// A unit is (utterance, 128*MT - (k-1) output rows): c1 computes 128*MT rows (the extra k-1 rows are c2's halo).
+// Each CTA keeps TWO units in flight on two "lanes" (own input slab, own M slab, own TMEM accumulators) and the
+// single MMA-issuing warp walks the software-pipelined job order
+//     c1(u0) | c1(u1) c2(u0) | c1(u2) c2(u1) | ... | c2(u_last)
+// so the epilogue of every job overlaps the MMAs of the next one.  Roles: warp 0 slab producer (TMA), warp 1
+// weight producer (bulk copies, both convs, job order), warp 2 MMA issuer, warp 3 TMEM allocator, warps 4-11
+// epilogue (two per TMEM lane quarter).
+#pragma once
+#include "conv_tc.cuh"
+
+namespace e2e {
+
+struct PairParams {
+  int T, B;
+  int panels;           // K panels of the C channels (C/64, or 1 for C = 32)
+  int nt;               // C (output columns of both convs)
+  int taps;             // k
+  int dil;              // dilation of c1
+  int a_rows;           // input slab rows per panel (multiple of box_rows, >= 128*MT + (k-1)*dil)
+  int box_rows;
+  int m_rows;           // M slab rows per panel (>= 128*MT + k-1, multiple of 8)
+  int r_out;            // valid output rows per unit = 128*MT - (k-1)
+  int tiles_per_chunk, n_chunks, n_stages, stage_bytes;   // weight ring geometry (same for c1 and c2)
+  int tiles_per_b, n_units;
+  float slope_mid;      // LeakyReLU between c1 and c2 (0.1)
+  float slope;          // LeakyReLU applied to out_act
+  float divisor;        // 0 = none
+  float res_inv_slope;  // 1 / slope of the stored input activation
+  const uint8_t* w1;    // packed weights of c1 / c2: [panel][tap][nt][rowb] swizzled images
+  const uint8_t* w2;
+  const float* bias1;
+  const float* bias2;
+  const __nv_bfloat16* res_act;  // == the kernel's input tensor (bf16 leaky_relu(x)), read for the residual
+  const float* sum_in;
+  float* out_f32;
+  __nv_bfloat16* out_act;
+};
+
+template <int ROWB, int MT>
+__global__ void __launch_bounds__(kConvThreads, 1)
+pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  constexpr int KS = ROWB / 32;
+  constexpr uint32_t ROW16 = ROWB >> 4;
+  constexpr uint32_t DESC_HI = ((8u * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
+  constexpr uint32_t SWZ = ROWB == 128 ? 7u : 3u;
+  constexpr int CH_PANEL = ROWB / 2;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int a_panel_bytes = p.a_rows * ROWB;
+  const int m_panel_bytes = p.m_rows * ROWB;
+  const int a_lane_bytes = p.panels * a_panel_bytes;
+  const int m_lane_bytes = p.panels * m_panel_bytes;
+  const int tile_bytes = p.nt * ROWB;
+  const int total_tiles = p.panels * p.taps;
+  const int h1 = (p.taps - 1) / 2 * p.dil, h2 = (p.taps - 1) / 2;
+  const int acc_cols = MT * p.nt;  // TMEM columns per accumulator; 4 accumulators: [lane][conv]
+
+  uint8_t* a_slab = smem;                                   // [2 lanes][panels][a_rows][ROWB]
+  uint8_t* m_slab = a_slab + 2 * a_lane_bytes;              // [2 lanes][panels][m_rows][ROWB]
+  uint8_t* ring = m_slab + 2 * m_lane_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.n_stages * p.stage_bytes);
+  uint64_t* a_full = bars;             // [2][4]
+  uint64_t* a_empty = a_full + 8;      // [2][4]
+  uint64_t* w_full = a_empty + 8;      // [kMaxStages]
+  uint64_t* w_empty = w_full + kMaxStages;
+  uint64_t* acc_full = w_empty + kMaxStages;  // [2][2]
+  uint64_t* acc_empty = acc_full + 4;         // [2][2]
+  uint64_t* m_full = acc_empty + 4;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(m_full + 2);
+
+  // units of this CTA: u_n = blockIdx.x + n * gridDim.x, n = 0 .. N-1
+  const int N = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    E2E_TR(0);
+    tma_prefetch_desc(&tm_in);
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < p.n_stages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kEpiWarps);
+    }
+    mbar_init(&m_full[0], kEpiWarps);
+    mbar_init(&m_full[1], kEpiWarps);
+    fence_mbar_init();
+  }
+  if (warp == 3) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) E2E_TR(1);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- input slab producer (TMA) ----------------
+      const int boxes = p.a_rows / p.box_rows;
+      for (int n = 0; n < N; ++n) {
+        const int u = blockIdx.x + n * gridDim.x;
+        const int b = u / p.tiles_per_b;
+        const int t0 = (u - b * p.tiles_per_b) * p.r_out;
+        const int ln = n & 1;
+        const uint32_t par = ((n >> 1) & 1) ^ 1;
+        for (int pn = 0; pn < p.panels; ++pn) {
+          mbar_wait(&a_empty[ln * 4 + pn], par, 0x100 + ln * 4 + pn);
+          mbar_arrive_expect_tx(&a_full[ln * 4 + pn], a_panel_bytes);
+          uint8_t* dst = a_slab + ln * a_lane_bytes + pn * a_panel_bytes;
+          for (int bx = 0; bx < boxes; ++bx)
+            tma_load_3d(dst + bx * p.box_rows * ROWB, &tm_in, pn * CH_PANEL, t0 - h2 - h1 + bx * p.box_rows, b,
+                        &a_full[ln * 4 + pn]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- weight producer: job order c1(u0) | c1(u1) c2(u0) | ... ----------------
+      uint32_t stage = 0, par = 1;
+      auto stream = [&](const uint8_t* wsrc) {
+        int first = 0;
+        for (int c = 0; c < p.n_chunks; ++c, first += p.tiles_per_chunk) {
+          mbar_wait(&w_empty[stage], par, 0x200 + stage);
+          const int ntile = min(p.tiles_per_chunk, total_tiles - first);
+          const uint32_t bytes = ntile * tile_bytes;
+          mbar_arrive_expect_tx(&w_full[stage], bytes);
+          bulk_load_1d(ring + stage * p.stage_bytes, wsrc + static_cast<size_t>(first) * tile_bytes, bytes,
+                       &w_full[stage]);
+          if (++stage == (uint32_t)p.n_stages) {
+            stage = 0;
+            par ^= 1;
+          }
+        }
+      };
+      for (int n = 0; n <= N; ++n) {
+        if (n < N) stream(p.w1);
+        if (n >= 1) stream(p.w2);
+      }
+    }
+  } else if (warp == 2) {
+    // ---------------- MMA issuer (warp-uniform loop, one elected lane issues) ----------------
+    const bool leader = elect_one();
+    const uint32_t idesc = umma_idesc_bf16(128, p.nt);
+    const uint32_t a_lo0 = ((smem_u32(a_slab) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t m_lo0 = ((smem_u32(m_slab) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t stage16 = p.stage_bytes >> 4, tile16 = tile_bytes >> 4;
+    uint32_t stage = 0, wpar = 0;
+    // one job = one convolution of one unit
+    auto job = [&](int n, int ci) {
+      const int ln = n & 1;
+      const uint32_t par = (n >> 1) & 1;
+      const uint32_t src_lo = ci == 0 ? a_lo0 + ln * (a_lane_bytes >> 4) : m_lo0 + ln * (m_lane_bytes >> 4);
+      const uint32_t panel16 = (ci == 0 ? a_panel_bytes : m_panel_bytes) >> 4;
+      const uint32_t tap_rows16 = (ci == 0 ? p.dil : 1) * ROW16;  // tap j reads rows shifted by j*d (c1) / j (c2)
+      mbar_wait(&acc_empty[ln * 2 + ci], par ^ 1, 0x300 + ln * 2 + ci);
+      if (ci == 1) mbar_wait(&m_full[ln], par, 0x380 + ln);  // c1's epilogue has written the whole M slab
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (ln * 2 + ci) * acc_cols;
+      int tap = 0, pn = 0, left = total_tiles;
+      uint32_t accum = 0;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        mbar_wait(&w_full[stage], wpar, 0x400 + stage);
+        tc_fence_after_sync();
+        const int ntile = min(p.tiles_per_chunk, left);
+        left -= ntile;
+        uint32_t b_lo = ring_lo + stage * stage16;
+        for (int i = 0; i < ntile; ++i, b_lo += tile16) {
+          if (tap == 0 && ci == 0) {
+            mbar_wait(&a_full[ln * 4 + pn], par, 0x500 + ln * 4 + pn);
+            tc_fence_after_sync();
+          }
+          const uint32_t s_lo = src_lo + pn * panel16 + tap * tap_rows16;
+          if (leader) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+#pragma unroll
+              for (int ks = 0; ks < KS; ++ks) {
+                const uint64_t da = (static_cast<uint64_t>(DESC_HI) << 32) | (s_lo + m * (128 * ROW16) + ks * 2);
+                const uint64_t db = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + ks * 2);
+                if (ks == 0)
+                  umma_bf16(d_tmem + m * p.nt, da, db, idesc, accum);
+                else
+                  umma_bf16_acc(d_tmem + m * p.nt, da, db, idesc);
+              }
+            }
+          }
+          accum = 1;
+          if (++tap == p.taps) {
+            if (ci == 0 && leader) umma_commit(&a_empty[ln * 4 + pn]);  // input panel consumed -> TMA may refill
+            tap = 0;
+            ++pn;
+          }
+        }
+        if (leader) umma_commit(&w_empty[stage]);
+        if (++stage == (uint32_t)p.n_stages) {
+          stage = 0;
+          wpar ^= 1;
+        }
+      }
+      if (leader) umma_commit(&acc_full[ln * 2 + ci]);
+    };
+    for (int n = 0; n <= N; ++n) {
+      if (n < N) job(n, 0);
+      if (n >= 1) job(n - 1, 1);
+      if (n == 0 && leader) E2E_TR(2);
+    }
+    if (leader) E2E_TR(4);
+  } else if (warp >= 4) {
+    // ---------------- epilogue ----------------
+    const int e = warp - 4;
+    const int quarter = e & 3;
+    const int half = e >> 2;
+    const int nchunk = p.nt >> 5;
+    const int items = MT * nchunk;
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+
+    // c1 epilogue: acc -> +bias1 -> leaky_relu -> bf16 -> M slab (zero outside the utterance)
+    auto epi1 = [&](int n) {
+      const int u = blockIdx.x + n * gridDim.x;
+      const int b = u / p.tiles_per_b;
+      const int t0 = (u - b * p.tiles_per_b) * p.r_out;
+      const int ln = n & 1;
+      const uint32_t par = (n >> 1) & 1;
+      uint8_t* mdst = m_slab + ln * m_lane_bytes;
+      mbar_wait(&acc_full[ln * 2 + 0], par, 0x600 + ln * 2);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (ln * 2 + 0) * acc_cols + lane_sel;
+      for (int item = half; item < items; item += 2) {
+        const int m = item / nchunk, cc = item - m * nchunk;
+        const int r = m * 128 + row_in_tile;   // M slab row
+        const int t = t0 - h2 + r;             // global time step of this row
+        const bool inside = t >= 0 && t < p.T;
+        uint32_t v[32];
+        tmem_ld_32x32(d_tmem + m * p.nt + cc * 32, v);
+        tmem_ld_wait();
+        const int n0 = cc * 32;
+        const float s = p.slope_mid;
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias1 + n0) + i);
+          float f0 = __uint_as_float(v[4 * i]) + bv.x, f1 = __uint_as_float(v[4 * i + 1]) + bv.y;
+          float f2 = __uint_as_float(v[4 * i + 2]) + bv.z, f3 = __uint_as_float(v[4 * i + 3]) + bv.w;
+          f0 = f0 > 0.f ? f0 : f0 * s;
+          f1 = f1 > 0.f ? f1 : f1 * s;
+          f2 = f2 > 0.f ? f2 : f2 * s;
+          f3 = f3 > 0.f ? f3 : f3 * s;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(f0, f1), h1v = __floats2bfloat162_rn(f2, f3);
+          pk[2 * i] = inside ? *reinterpret_cast<uint32_t*>(&h0) : 0u;
+          pk[2 * i + 1] = inside ? *reinterpret_cast<uint32_t*>(&h1v) : 0u;
+        }
+        // 32 channels = four 16-byte chunks of this row in panel (n0 / CH_PANEL)
+        const int pn = n0 / CH_PANEL;
+        const int chunk0 = (n0 % CH_PANEL) / 8;
+        uint8_t* prow = mdst + pn * m_panel_bytes;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t off = static_cast<uint32_t>(r) * ROWB + (chunk0 + q) * 16;
+          off ^= ((off >> 7) & SWZ) << 4;
+          *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      tc_fence_before_sync();
+      fence_proxy_async_smem();  // the M slab is read by the tensor core through the async proxy
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&acc_empty[ln * 2 + 0]);
+        mbar_arrive(&m_full[ln]);
+      }
+    };
+
+    // c2 epilogue: acc + bias2 + residual (+ running sum, / divisor) -> global
+    auto epi2 = [&](int n) {
+      const int u = blockIdx.x + n * gridDim.x;
+      const int b = u / p.tiles_per_b;
+      const int t0 = (u - b * p.tiles_per_b) * p.r_out;
+      const int ln = n & 1;
+      const uint32_t par = (n >> 1) & 1;
+      uint4 rqa[4], rqb[4];
+      auto prefetch = [&](int item, uint4 (&dst)[4]) {
+        const int m = item / nchunk, cc = item - m * nchunk;
+        const int o = m * 128 + row_in_tile;
+        const int t = t0 + o;
+        if (item < items && o < p.r_out && t < p.T) {
+          const uint4* src =
+              reinterpret_cast<const uint4*>(p.res_act + (static_cast<size_t>(b) * p.T + t) * p.nt + cc * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = src[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      prefetch(half, rqa);
+      prefetch(half + 2, rqb);
+      mbar_wait(&acc_full[ln * 2 + 1], par, 0x700 + ln * 2);
+      tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + (ln * 2 + 1) * acc_cols + lane_sel;
+      auto process = [&](int item, uint4 (&rq)[4]) {
+        const int m = item / nchunk, cc = item - m * nchunk;
+        const int o = m * 128 + row_in_tile;
+        const int t = t0 + o;
+        const bool valid = o < p.r_out && t < p.T;
+        uint32_t v[32];
+        tmem_ld_32x32(d_tmem + m * p.nt + cc * 32, v);
+        tmem_ld_wait();
+        float f[32];
+        const int n0 = cc * 32;
+        const float inv = p.res_inv_slope;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t w4[4] = {rq[i].x, rq[i].y, rq[i].z, rq[i].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
+            lo = lo > 0.f ? lo : lo * inv;
+            hi = hi > 0.f ? hi : hi * inv;
+            f[8 * i + 2 * j] = lo;
+            f[8 * i + 2 * j + 1] = hi;
+          }
+        }
+        prefetch(item + 4, rq);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias2 + n0) + i);
+          f[4 * i] += __uint_as_float(v[4 * i]) + bv.x;
+          f[4 * i + 1] += __uint_as_float(v[4 * i + 1]) + bv.y;
+          f[4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bv.z;
+          f[4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bv.w;
+        }
+        if (valid) {
+          const size_t off = (static_cast<size_t>(b) * p.T + t) * p.nt + n0;
+          if (p.sum_in) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 sv = __ldg(reinterpret_cast<const float4*>(p.sum_in + off) + i);
+              f[4 * i] += sv.x; f[4 * i + 1] += sv.y; f[4 * i + 2] += sv.z; f[4 * i + 3] += sv.w;
+            }
+          }
+          if (p.divisor != 0.f) {
+            const float dv = p.divisor;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = f[i] / dv;
+          }
+          if (p.out_f32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              reinterpret_cast<float4*>(p.out_f32 + off)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          }
+          if (p.out_act) {
+            const float s = p.slope;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float a = f[8 * i + 2 * j], c = f[8 * i + 2 * j + 1];
+                a = a > 0.f ? a : a * s;
+                c = c > 0.f ? c : c * s;
+                __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              reinterpret_cast<uint4*>(p.out_act + off)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+      };
+      for (int item = half; item < items; item += 4) {
+        process(item, rqa);
+        if (item + 2 < items) process(item + 2, rqb);
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ln * 2 + 1]);
+    };
+
+    for (int n = 0; n <= N; ++n) {
+      if (n < N) epi1(n);
+      if (n >= 1) epi2(n - 1);
+    }
+  }
+
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 3) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512);
+  }
+  if (threadIdx.x == 0) E2E_TR(7);
+}
+
+}  // namespace e2e

@@ -1,12 +1,13 @@
 // HiFi-GAN generator on B200: layer table, weight packing, launch plans and the forward pass.
 // Mirrors the structure of the reference generator (e2e_tts/models/vocoder/generator.py:13-53 and
 // layers.py:10-69) as a list of tcgen05 convolution launches plus two small CUDA-core kernels.
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <string>
 #include <vector>
 #include "../../include/e2e_tts_b200.h"
-#include "conv_host.cuh"
+#include "pair_host.cuh"
 #include "small_kernels.cuh"
 
 using namespace e2e;
@@ -27,9 +28,10 @@ struct Layer {
 };
 
 struct Op {
-  int kind;   // 0 = mel_to_act, 1 = conv_tc, 2 = post
+  int kind;   // 0 = mel_to_act, 1 = conv_tc, 2 = post, 3 = fused residual pair
   int layer;  // index into layers
   ConvPlan plan;
+  PairPlan pair;
 };
 
 struct PlanKey {
@@ -65,6 +67,7 @@ struct e2e_voc {
   int hop = 1;
   int n_sms = 148;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // one-shot profiling events
+  int last_launches = 0;
 };
 
 static int pick_nt(int cout) { return cout >= 256 ? 256 : cout; }
@@ -184,6 +187,8 @@ extern "C" int e2e_voc_create(const e2e_voc_config* cfg, e2e_voc** out) {
   cudaDeviceGetAttribute(&v->n_sms, cudaDevAttrMultiProcessorCount, dev);
   if (v->n_sms < 1) v->n_sms = 148;
   int rc_init = conv_kernels_init();
+  if (rc_init) return rc_init;
+  rc_init = pair_kernels_init();
   if (rc_init) return rc_init;
   *out = v.release();
   return 0;
@@ -332,7 +337,7 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
   int mt = 1;
   double best = 0.0;
   for (int cand = 1; cand <= 4; cand <<= 1) {
-    if (cand * s.nt > 512) break;
+    if (2 * cand * s.nt > 512 && cand > 1) break;  // keep two TMEM accumulator sets (epilogue overlaps MMAs)
     const long long units = (long long)((T + 128 * cand - 1) / (128 * cand)) * n_tiles * B;
     const long long rounds = (units + v->n_sms - 1) / v->n_sms;
     // useful rows / rows the busiest CTA pays for
@@ -354,6 +359,35 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
   p.sum_in = sum_in;
   p.out_f32 = out_f32;
   p.out_act = out_act;
+  p.slope = slope;
+  p.divisor = divisor;
+  ops.push_back(op);
+  return 0;
+}
+
+// One fused launch for  x + c2(lrelu(c1(lrelu(x))))  (pair_tc.cuh).  `in` holds bf16 leaky_relu(x, 0.1).
+static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B, int T, const __nv_bfloat16* in,
+                        const float* sum_in, float* out_f32, __nv_bfloat16* out_act, float slope, float divisor) {
+  const Layer& L1 = v->layers[l1];
+  const Layer& L2 = v->layers[l2];
+  Op op;
+  op.kind = 3;
+  op.layer = l1;
+  int rc = plan_pair(op.pair, L1.cin, L1.k, L1.dil, B, T, v->n_sms);
+  if (rc) return rc;
+  PairParams& p = op.pair.p;
+  rc = make_act_tensor_map(&op.pair.tm, in, B, T, L1.cin, op.pair.rowb / 2, p.box_rows);
+  if (rc) return rc;
+  p.w1 = L1.d_w;
+  p.w2 = L2.d_w;
+  p.bias1 = L1.d_bias;
+  p.bias2 = L2.d_bias;
+  p.res_act = in;
+  p.res_inv_slope = 10.0f;
+  p.sum_in = sum_in;
+  p.out_f32 = out_f32;
+  p.out_act = out_act;
+  p.slope_mid = 0.1f;
   p.slope = slope;
   p.divisor = divisor;
   ops.push_back(op);
@@ -389,11 +423,18 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
       const std::string base = "resblocks." + std::to_string(i * c.num_kernels + j);
       const int nd = c.num_dilations[j];
       const __nv_bfloat16* ain = bf.A0;
+      const int chs = v->layers[v->by_name[base + (c.resblock == 1 ? ".convs1.0" : ".convs.0")]].cin;
+      const int ks = c.resblock_kernel_sizes[j];
+      // ResBlock1 pairs run fused when the channel count allows (stages with C <= 128); the fused kernel reads
+      // halo rows of its input from neighbouring tiles, so it ping-pongs between two output buffers (A1, M)
+      // instead of updating in place.
+      bool fused = c.resblock == 1 && std::getenv("E2E_NO_PAIR_FUSION") == nullptr;
+      for (int m = 0; m < nd && fused; ++m) fused = pair_supported(chs, ks, c.resblock_dilation_sizes[j][m]);
       for (int m = 0; m < nd; ++m) {
         const bool last = m + 1 == nd;
         // where does x_new = conv(...) + x go?
         float* of32 = nullptr;
-        __nv_bfloat16* oact = bf.A1;
+        __nv_bfloat16* oact = fused ? ((m & 1) ? bf.M : bf.A1) : bf.A1;
         const float* sum_in = nullptr;
         float divisor = 0.f, slope = kSlope;
         if (last) {
@@ -407,19 +448,26 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
             slope = out_slope;
           }
         }
-        if (c.resblock == 1) {
+        if (fused) {
+          rc = make_pair_op(v, ops, v->by_name[base + ".convs1." + std::to_string(m)],
+                            v->by_name[base + ".convs2." + std::to_string(m)], B, Ts, ain, sum_in, of32, oact, slope,
+                            divisor);
+          if (rc) return rc;
+          ain = oact;
+        } else if (c.resblock == 1) {
           rc = make_conv_op(v, ops, v->by_name[base + ".convs1." + std::to_string(m)], B, Ts, ain, nullptr, nullptr,
                             nullptr, bf.M, kSlope, 0.f);
           if (rc) return rc;
           rc = make_conv_op(v, ops, v->by_name[base + ".convs2." + std::to_string(m)], B, Ts, bf.M, ain, sum_in,
                             of32, oact, slope, divisor);
           if (rc) return rc;
+          ain = bf.A1;
         } else {
           rc = make_conv_op(v, ops, v->by_name[base + ".convs." + std::to_string(m)], B, Ts, ain, ain, sum_in, of32,
                             oact, slope, divisor);
           if (rc) return rc;
+          ain = bf.A1;
         }
-        ain = bf.A1;
       }
     }
     stage_in = bf.Y;
@@ -435,8 +483,9 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
 
 extern "C" int e2e_voc_launches_per_forward(const e2e_voc* v) {
   if (!v) return -1;
+  if (v->last_launches > 0) return v->last_launches;  // what the last forward actually enqueued
   const e2e_voc_config& c = v->cfg;
-  int n = 3;  // mel_to_act, conv_pre, conv_post
+  int n = 3;  // mel_to_act, conv_pre, conv_post (unfused estimate before the first forward)
   for (int i = 0; i < c.num_upsamples; ++i) {
     n += 1;
     for (int j = 0; j < c.num_kernels; ++j) n += c.num_dilations[j] * (c.resblock == 1 ? 2 : 1);
@@ -467,7 +516,7 @@ extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t
   const std::vector<Op>& ops = it->second;
   size_t first_conv = ops.size(), last_conv = 0;
   for (size_t i = 0; i < ops.size(); ++i)
-    if (ops[i].kind == 1) {
+    if (ops[i].kind == 1 || ops[i].kind == 3) {
       first_conv = i < first_conv ? i : first_conv;
       last_conv = i;
     }
@@ -481,6 +530,9 @@ extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t
     } else if (op.kind == 1) {
       int rc = launch_conv(op.plan, st);
       if (rc) return rc;
+    } else if (op.kind == 3) {
+      int rc = launch_pair(op.pair, st);
+      if (rc) return rc;
     } else {
       const Layer& L = v->layers[op.layer];
       const int Tout = T * v->hop;
@@ -491,6 +543,7 @@ extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t
     if (oi == last_conv && v->ev_end) cudaEventRecord(v->ev_end, st);
   }
   v->ev_begin = v->ev_end = nullptr;
+  v->last_launches = (int)ops.size();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("e2e_voc_forward launch: ") + cudaGetErrorString(e));
   return 0;
