@@ -8,7 +8,7 @@
 A "step" is one pass of the vocoder hot path (HifiGan.forward: mel -> waveform) over one batch of synthetic
 log-mel-like input with random-init weights of the reference's default HiFi-GAN V1 config.  Workload at every N:
 BASELINE.json configs[1] per GPU — 16 utterances x 5 s (T = 431 mel frames -> 110 336 samples each), bf16 tensor-core
-operands with fp32 accumulation and an fp32 residual stream.  N > 1 is weak scaling: every rank synthesises its own
+operands with fp32 accumulation, bf16 activation+residual stream, fp32 resblock sum.  N > 1 is weak scaling: every rank synthesises its own
 16 utterances (no data-path collective) and the step ends with the NCCL gather of all waveforms on rank 0
 (SURVEY.md §8 e).  Prints ONE JSON line on rank 0.
 
@@ -265,7 +265,7 @@ def main():
         "data": "synthetic",
         "config": {"workload": "cfg2 per GPU: 16 utterances x 5 s (T=431 -> 110336 samples), HiFi-GAN V1 default config "
                                "(model_config.yaml:75-82), random-init weights (fan-in-scaled 'strong' regime), bf16 "
-                               "operands / fp32 accumulate / fp32 residual stream",
+                               "operands / fp32 accumulate / bf16 activation+residual stream / fp32 resblock sum",
                    "global_batch": world * B, "mel_frames": T, "parallelism": "batch-sharded x%d + gather" % world,
                    "l2": "no flush: per-step working set ~1.1 GB >> 126 MB L2; inputs rotate over %d buffers" % n_in},
         "clocks": clocks,

@@ -90,6 +90,9 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
 
   if (threadIdx.x == 0) {
     E2E_TR(0);
+#ifdef E2E_TRACE
+    if (blockIdx.x < 512) g_trace[blockIdx.x][8] = g_trace[blockIdx.x][9] = g_trace[blockIdx.x][10] = g_trace[blockIdx.x][11] = 0;
+#endif
     tma_prefetch_desc(&tm_in);
     for (int i = 0; i < 8; ++i) {
       mbar_init(&a_full[i], 1);
@@ -177,22 +180,43 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
       const uint32_t src_lo = ci == 0 ? a_lo0 + ln * (a_lane_bytes >> 4) : m_lo0 + ln * (m_lane_bytes >> 4);
       const uint32_t panel16 = (ci == 0 ? a_panel_bytes : m_panel_bytes) >> 4;
       const uint32_t tap_rows16 = (ci == 0 ? p.dil : 1) * ROW16;  // tap j reads rows shifted by j*d (c1) / j (c2)
+#ifdef E2E_TRACE
+      unsigned long long tq = gtime_ns();
+#endif
       mbar_wait(&acc_empty[ln * 2 + ci], par ^ 1, 0x300 + ln * 2 + ci);
+#ifdef E2E_TRACE
+      if (leader && blockIdx.x < 512) { const unsigned long long t2 = gtime_ns(); g_trace[blockIdx.x][8] += t2 - tq; tq = t2; }
+#endif
       if (ci == 1) mbar_wait(&m_full[ln], par, 0x380 + ln);  // c1's epilogue has written the whole M slab
+#ifdef E2E_TRACE
+      if (leader && blockIdx.x < 512) g_trace[blockIdx.x][9] += gtime_ns() - tq;
+#endif
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + (ln * 2 + ci) * acc_cols;
       int tap = 0, pn = 0, left = total_tiles;
       uint32_t accum = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
+#ifdef E2E_TRACE
+        const unsigned long long tw = gtime_ns();
+#endif
         mbar_wait(&w_full[stage], wpar, 0x400 + stage);
         tc_fence_after_sync();
+#ifdef E2E_TRACE
+        if (leader && blockIdx.x < 512) g_trace[blockIdx.x][10] += gtime_ns() - tw;
+#endif
         const int ntile = min(p.tiles_per_chunk, left);
         left -= ntile;
         uint32_t b_lo = ring_lo + stage * stage16;
         for (int i = 0; i < ntile; ++i, b_lo += tile16) {
           if (tap == 0 && ci == 0) {
+#ifdef E2E_TRACE
+            const unsigned long long ta = gtime_ns();
+#endif
             mbar_wait(&a_full[ln * 4 + pn], par, 0x500 + ln * 4 + pn);
             tc_fence_after_sync();
+#ifdef E2E_TRACE
+            if (leader && blockIdx.x < 512) g_trace[blockIdx.x][11] += gtime_ns() - ta;
+#endif
           }
           const uint32_t s_lo = src_lo + pn * panel16 + tap * tap_rows16;
           if (leader) {

@@ -248,6 +248,20 @@ int main(int argc, char** argv) {
   ms /= reps;
   const double flops = 2.0 * 2.0 * c.B * c.T * (double)c.C * c.k * c.C;
   printf("  time %.4f ms  -> %.1f TFLOP/s (algorithmic)\n", ms, flops / ms * 1e-9);
+#ifdef E2E_TRACE
+  {
+    static unsigned long long tr[512][12];
+    launch_pair(plan, 0);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(tr, g_trace, sizeof(tr)));
+    printf("  trace: cta | kernel us | MMA-thread waits (us): acc_empty m_full w_full a_full | units\n");
+    for (int i = 0; i < (int)plan.grid.x && i < 512; i += 49) {
+      const int nu = (p.n_units - i + plan.grid.x - 1) / plan.grid.x;
+      printf("  %5d | %8.2f | %8.2f %8.2f %8.2f %8.2f | %d\n", i, (tr[i][7] - tr[i][0]) * 1e-3, tr[i][8] * 1e-3,
+             tr[i][9] * 1e-3, tr[i][10] * 1e-3, tr[i][11] * 1e-3, nu);
+    }
+  }
+#endif
   const bool ok = bad == 0 && bad2 == 0;
   printf("[pair %d] %s\n", id, ok ? "PASS" : "FAIL");
   return ok ? 0 : 1;
