@@ -284,15 +284,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
         if (p.res_act && item < items && t < p.T) {
           const uint4* src = reinterpret_cast<const uint4*>(
               p.res_act + (static_cast<size_t>(b) * p.T + t) * p.n_total + nti * p.nt + cc * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = src[i];  // plain loads: the buffer may be updated in place
+          ld_global_256(src, dst[0], dst[1]);  // plain (coherent) loads: the buffer may be updated in place
+          ld_global_256(src + 2, dst[2], dst[3]);
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
         }
       };
+      uint4 sq[8];  // running-sum prefetch, one item ahead
+      auto prefetch_sum = [&](int item) {
+        const int m = item / nchunk, cc = item - m * nchunk;
+        const int t = t0 + m * 128 + row_in_tile;
+        if (p.sum_in && item < items && t < p.T) {
+          const float* src = p.sum_in + (static_cast<size_t>(b) * p.T + t) * p.n_total + nti * p.nt + cc * 32;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ld_global_256(src + 8 * i, sq[2 * i], sq[2 * i + 1]);
+        }
+      };
       prefetch(half, rqa);      // overlaps the MMAs of this unit
       prefetch(half + 2, rqb);
+      prefetch_sum(half);
       mbar_wait(&acc_full[acc], apar, 0x600 + acc);
       tc_fence_after_sync();
       if (it == 0 && threadIdx.x == 128) E2E_TR(5);
@@ -334,10 +345,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
           if (p.sum_in) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 s = __ldg(reinterpret_cast<const float4*>(p.sum_in + off) + i);
-              f[4 * i] += s.x; f[4 * i + 1] += s.y; f[4 * i + 2] += s.z; f[4 * i + 3] += s.w;
+              f[4 * i] += __uint_as_float(sq[i].x); f[4 * i + 1] += __uint_as_float(sq[i].y);
+              f[4 * i + 2] += __uint_as_float(sq[i].z); f[4 * i + 3] += __uint_as_float(sq[i].w);
             }
           }
+          prefetch_sum(item + 2);
           if (p.divisor != 0.f) {
             const float dv = p.divisor;
 #pragma unroll
@@ -345,24 +357,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
           }
           if (p.out_f32) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              reinterpret_cast<float4*>(p.out_f32 + off)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            for (int i = 0; i < 4; ++i)
+              st_global_256(p.out_f32 + off + 8 * i,
+                            make_uint4(__float_as_uint(f[8 * i]), __float_as_uint(f[8 * i + 1]),
+                                       __float_as_uint(f[8 * i + 2]), __float_as_uint(f[8 * i + 3])),
+                            make_uint4(__float_as_uint(f[8 * i + 4]), __float_as_uint(f[8 * i + 5]),
+                                       __float_as_uint(f[8 * i + 6]), __float_as_uint(f[8 * i + 7])));
           }
           if (p.out_act) {
             const float s = p.slope;
+            uint32_t pk[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float a = f[8 * i + 2 * j], c = f[8 * i + 2 * j + 1];
-                a = a > 0.f ? a : a * s;
-                c = c > 0.f ? c : c * s;
-                __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
-                pk[j] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              reinterpret_cast<uint4*>(p.out_act + off)[i] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int i = 0; i < 16; ++i) {
+              float a = f[2 * i], c = f[2 * i + 1];
+              a = a > 0.f ? a : a * s;
+              c = c > 0.f ? c : c * s;
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
+              pk[i] = *reinterpret_cast<uint32_t*>(&h);
             }
+            st_global_256(p.out_act + off, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+            st_global_256(p.out_act + off + 16, make_uint4(pk[8], pk[9], pk[10], pk[11]),
+                          make_uint4(pk[12], pk[13], pk[14], pk[15]));
           }
         }
       };

@@ -213,6 +213,20 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 256-bit global accesses (LDG.E.256 / STG.E.256, 32-byte aligned): a lane moves one full 32-byte sector per
+// instruction, which halves the L1TEX sector work of the row-per-lane epilogue accesses.
+__device__ __forceinline__ void ld_global_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 // Byte offset -> swizzled byte offset inside a 1024-B-aligned buffer (Swizzle<B,4,3>): mask 7 = 128B,
 // 3 = 64B.  Used by everything that writes operand bytes with ordinary stores (weight packer, fused epilogues).
 __host__ __device__ __forceinline__ uint32_t swizzle_off(uint32_t off, uint32_t mask) {
