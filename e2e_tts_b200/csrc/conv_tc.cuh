@@ -19,12 +19,13 @@
 //   warp 2   MMA issuer     : one thread issues tcgen05.mma; the (M tile, K step) loops are unrolled and the
 //                             descriptors are advanced by adding to their low word only
 //   warp 3   TMEM allocator
-//   warps 4-11 epilogue     : tcgen05.ld the fp32 accumulators (two warps per TMEM lane quarter), fuse bias,
-//                             residual add (prefetched while the MMAs run), resblock sum, /3, LeakyReLU, casts
+//   warps 4-19 epilogue     : tcgen05.ld the fp32 accumulators (four warps per TMEM lane quarter, 16-column
+//                             items), fuse bias, residual add (prefetched while the MMAs run), resblock sum,
+//                             /3, LeakyReLU, casts (epilogue.cuh)
 // Accumulators are double-buffered in TMEM when 2*MT*nt <= 512 columns, so the epilogue of unit i overlaps
 // the MMAs of unit i+1.
 #pragma once
-#include "ptx.cuh"
+#include "epilogue.cuh"
 
 namespace e2e {
 
@@ -32,8 +33,6 @@ constexpr int kMaxTaps = 16;
 constexpr int kMaxNTiles = 16;
 constexpr int kMaxPanelSlots = 8;
 constexpr int kMaxStages = 8;
-constexpr int kConvThreads = 384;
-constexpr int kEpiWarps = 8;
 
 struct ConvParams {
   int T;                // time steps per utterance (rows); input and output have the same row count
@@ -263,9 +262,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     const int e = warp - 4;
     const int quarter = e & 3;  // == warp % 4: the TMEM lanes this warp may read
-    const int half = e >> 2;
-    const int nchunk = p.nt >> 5;
-    const int items = MT * nchunk;  // (m tile, 32-column chunk) pairs; this warp takes items with item%2 == half
+    const int part = e >> 2;    // this warp takes the items with item % 4 == part
+    const int nchunk = p.nt >> 4;
+    const int items = MT * nchunk;  // (m tile, 16-column chunk) pairs
+    const int row_in_tile = quarter * 32 + lane;
+    EpiOut eo;
+    eo.bias = p.bias;
+    eo.sum_in = p.sum_in;
+    eo.out_f32 = p.out_f32;
+    eo.out_act = p.out_act;
+    eo.slope = p.slope;
+    eo.divisor = p.divisor;
+    eo.inv = p.res_inv_slope;
     uint32_t it = 0, acc = 0, apar = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
       const int nti = u % p.n_tiles;
@@ -273,117 +281,57 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
       const int b = tb / p.tiles_per_b;
       const int t0 = (tb - b * p.tiles_per_b) * (128 * MT);
       const uint32_t d_tmem = tmem_base + acc * (MT * p.nt) + (static_cast<uint32_t>(quarter * 32) << 16);
-      const int row_in_tile = quarter * 32 + lane;
 
-      // Residual: 32 bf16 of this thread's row per item, prefetched two items ahead (loads of item i+2 are in
-      // flight while item i is processed), so the L2/HBM latency is off the critical path.
-      uint4 rqa[4], rqb[4];
-      auto prefetch = [&](int item, uint4 (&dst)[4]) {
+      // residual (16 bf16) two items ahead, running sum (16 fp32) one item ahead
+      uint4 rqa[2], rqb[2], sq[4];
+      auto item_off = [&](int item, int& n0, bool& valid) -> size_t {
         const int m = item / nchunk, cc = item - m * nchunk;
         const int t = t0 + m * 128 + row_in_tile;
-        if (p.res_act && item < items && t < p.T) {
-          const uint4* src = reinterpret_cast<const uint4*>(
-              p.res_act + (static_cast<size_t>(b) * p.T + t) * p.n_total + nti * p.nt + cc * 32);
-          ld_global_256(src, dst[0], dst[1]);  // plain (coherent) loads: the buffer may be updated in place
-          ld_global_256(src + 2, dst[2], dst[3]);
+        valid = item < items && t < p.T;
+        n0 = nti * p.nt + cc * 16;
+        return (static_cast<size_t>(b) * p.T + (valid ? t : 0)) * p.n_total + n0;
+      };
+      auto prefetch = [&](int item, uint4 (&dst)[2]) {
+        int n0;
+        bool valid;
+        const size_t off = item_off(item, n0, valid);
+        if (p.res_act && valid) {
+          ld_global_256(p.res_act + off, dst[0], dst[1]);  // plain loads: the buffer may be updated in place
         } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+          dst[0] = dst[1] = make_uint4(0u, 0u, 0u, 0u);
         }
       };
-      uint4 sq[8];  // running-sum prefetch, one item ahead
       auto prefetch_sum = [&](int item) {
-        const int m = item / nchunk, cc = item - m * nchunk;
-        const int t = t0 + m * 128 + row_in_tile;
-        if (p.sum_in && item < items && t < p.T) {
-          const float* src = p.sum_in + (static_cast<size_t>(b) * p.T + t) * p.n_total + nti * p.nt + cc * 32;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) ld_global_256(src + 8 * i, sq[2 * i], sq[2 * i + 1]);
+        int n0;
+        bool valid;
+        const size_t off = item_off(item, n0, valid);
+        if (p.sum_in && valid) {
+          ld_global_256(p.sum_in + off, sq[0], sq[1]);
+          ld_global_256(p.sum_in + off + 8, sq[2], sq[3]);
         }
       };
-      prefetch(half, rqa);      // overlaps the MMAs of this unit
-      prefetch(half + 2, rqb);
-      prefetch_sum(half);
+      prefetch(part, rqa);  // overlaps the MMAs of this unit
+      prefetch(part + 4, rqb);
+      prefetch_sum(part);
       mbar_wait(&acc_full[acc], apar, 0x600 + acc);
       tc_fence_after_sync();
       if (it == 0 && threadIdx.x == 128) E2E_TR(5);
 
-      auto process = [&](int item, uint4 (&rq)[4]) {
+      auto process = [&](int item, uint4 (&rq)[2]) {
         const int m = item / nchunk, cc = item - m * nchunk;
-        const int t = t0 + m * 128 + row_in_tile;
-        const bool valid = t < p.T;
-        uint32_t v[32];
-        tmem_ld_32x32(d_tmem + m * p.nt + cc * 32, v);
+        int n0;
+        bool valid;
+        const size_t off = item_off(item, n0, valid);
+        uint32_t v[16];
+        tmem_ld_32x16(d_tmem + m * p.nt + cc * 16, v);
         tmem_ld_wait();
-        float f[32];
-        const int n0 = nti * p.nt + cc * 32;
-        const float inv = p.res_inv_slope;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t w4[4] = {rq[i].x, rq[i].y, rq[i].z, rq[i].w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            // bf16 -> fp32 is a 16-bit shift; x = a > 0 ? a : a / slope
-            float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
-            lo = lo > 0.f ? lo : lo * inv;
-            hi = hi > 0.f ? hi : hi * inv;
-            f[8 * i + 2 * j] = lo;
-            f[8 * i + 2 * j + 1] = hi;
-          }
-        }
-        prefetch(item + 4, rq);  // refill this slot for the item after next
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
-          f[4 * i] += __uint_as_float(v[4 * i]) + bv.x;
-          f[4 * i + 1] += __uint_as_float(v[4 * i + 1]) + bv.y;
-          f[4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bv.z;
-          f[4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bv.w;
-        }
-        if (valid) {
-          const size_t off = (static_cast<size_t>(b) * p.T + t) * p.n_total + n0;
-          if (p.sum_in) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              f[4 * i] += __uint_as_float(sq[i].x); f[4 * i + 1] += __uint_as_float(sq[i].y);
-              f[4 * i + 2] += __uint_as_float(sq[i].z); f[4 * i + 3] += __uint_as_float(sq[i].w);
-            }
-          }
-          prefetch_sum(item + 2);
-          if (p.divisor != 0.f) {
-            const float dv = p.divisor;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = f[i] / dv;
-          }
-          if (p.out_f32) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              st_global_256(p.out_f32 + off + 8 * i,
-                            make_uint4(__float_as_uint(f[8 * i]), __float_as_uint(f[8 * i + 1]),
-                                       __float_as_uint(f[8 * i + 2]), __float_as_uint(f[8 * i + 3])),
-                            make_uint4(__float_as_uint(f[8 * i + 4]), __float_as_uint(f[8 * i + 5]),
-                                       __float_as_uint(f[8 * i + 6]), __float_as_uint(f[8 * i + 7])));
-          }
-          if (p.out_act) {
-            const float s = p.slope;
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float a = f[2 * i], c = f[2 * i + 1];
-              a = a > 0.f ? a : a * s;
-              c = c > 0.f ? c : c * s;
-              __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            st_global_256(p.out_act + off, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
-            st_global_256(p.out_act + off + 16, make_uint4(pk[8], pk[9], pk[10], pk[11]),
-                          make_uint4(pk[12], pk[13], pk[14], pk[15]));
-          }
-        }
+        epi_finish16(v, rq, sq, eo, n0, off, valid);
+        prefetch(item + 8, rq);   // refill this slot for the item after next
+        prefetch_sum(item + 4);   // (sq was consumed above)
       };
-      for (int item = half; item < items; item += 4) {
+      for (int item = part; item < items; item += 8) {
         process(item, rqa);
-        if (item + 2 < items) process(item + 2, rqb);
+        if (item + 4 < items) process(item + 4, rqb);
       }
       // all of this warp's TMEM reads of the unit are complete (tcgen05.wait::ld above): release the accumulator
       tc_fence_before_sync();

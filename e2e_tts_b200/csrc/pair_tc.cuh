@@ -16,8 +16,8 @@
 // single MMA-issuing warp walks the software-pipelined job order
 //     c1(u0) | c1(u1) c2(u0) | c1(u2) c2(u1) | ... | c2(u_last)
 // so the epilogue of every job overlaps the MMAs of the next one.  Roles: warp 0 slab producer (TMA), warp 1
-// weight producer (bulk copies, both convs, job order), warp 2 MMA issuer, warp 3 TMEM allocator, warps 4-11
-// epilogue (two per TMEM lane quarter).
+// weight producer (bulk copies, both convs, job order), warp 2 MMA issuer, warp 3 TMEM allocator, warps 4-19
+// epilogue (four per TMEM lane quarter, 16-column items, epilogue.cuh).
 #pragma once
 #include "conv_tc.cuh"
 
@@ -91,7 +91,9 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
   if (threadIdx.x == 0) {
     E2E_TR(0);
 #ifdef E2E_TRACE
-    if (blockIdx.x < 512) g_trace[blockIdx.x][8] = g_trace[blockIdx.x][9] = g_trace[blockIdx.x][10] = g_trace[blockIdx.x][11] = 0;
+    if (blockIdx.x < 512)
+      for (int i = 2; i < 12; ++i)
+        if (i != 4 && i != 7) g_trace[blockIdx.x][i] = 0;
 #endif
     tma_prefetch_desc(&tm_in);
     for (int i = 0; i < 8; ++i) {
@@ -251,18 +253,25 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
     for (int n = 0; n <= N; ++n) {
       if (n < N) job(n, 0);
       if (n >= 1) job(n - 1, 1);
-      if (n == 0 && leader) E2E_TR(2);
     }
     if (leader) E2E_TR(4);
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
     const int e = warp - 4;
     const int quarter = e & 3;
-    const int half = e >> 2;
-    const int nchunk = p.nt >> 5;
-    const int items = MT * nchunk;
+    const int part = e >> 2;        // this warp takes the items with item % 4 == part
+    const int nchunk = p.nt >> 4;
+    const int items = MT * nchunk;  // == 8 for every supported (C, MT): exactly two items per warp
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    EpiOut eo;
+    eo.bias = p.bias2;
+    eo.sum_in = p.sum_in;
+    eo.out_f32 = p.out_f32;
+    eo.out_act = p.out_act;
+    eo.slope = p.slope;
+    eo.divisor = p.divisor;
+    eo.inv = p.res_inv_slope;
 
     // c1 epilogue: acc -> +bias1 -> leaky_relu -> bf16 -> M slab (zero outside the utterance)
     auto epi1 = [&](int n) {
@@ -272,39 +281,42 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
       const int ln = n & 1;
       const uint32_t par = (n >> 1) & 1;
       uint8_t* mdst = m_slab + ln * m_lane_bytes;
+#ifdef E2E_TRACE
+      const unsigned long long te0 = gtime_ns();
+#endif
       mbar_wait(&acc_full[ln * 2 + 0], par, 0x600 + ln * 2);
       tc_fence_after_sync();
+#ifdef E2E_TRACE
+      const unsigned long long te1 = gtime_ns();
+#endif
       const uint32_t d_tmem = tmem_base + (ln * 2 + 0) * acc_cols + lane_sel;
-      for (int item = half; item < items; item += 2) {
+      for (int item = part; item < items; item += 4) {
         const int m = item / nchunk, cc = item - m * nchunk;
         const int r = m * 128 + row_in_tile;   // M slab row
         const int t = t0 - h2 + r;             // global time step of this row
         const bool inside = t >= 0 && t < p.T;
-        uint32_t v[32];
-        tmem_ld_32x32(d_tmem + m * p.nt + cc * 32, v);
+        uint32_t v[16];
+        tmem_ld_32x16(d_tmem + m * p.nt + cc * 16, v);
         tmem_ld_wait();
-        const int n0 = cc * 32;
+        const int n0 = cc * 16;
         const float s = p.slope_mid;
-        uint32_t pk[16];
+        uint32_t pk[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias1 + n0) + i);
-          float f0 = __uint_as_float(v[4 * i]) + bv.x, f1 = __uint_as_float(v[4 * i + 1]) + bv.y;
-          float f2 = __uint_as_float(v[4 * i + 2]) + bv.z, f3 = __uint_as_float(v[4 * i + 3]) + bv.w;
-          f0 = f0 > 0.f ? f0 : f0 * s;
-          f1 = f1 > 0.f ? f1 : f1 * s;
-          f2 = f2 > 0.f ? f2 : f2 * s;
-          f3 = f3 > 0.f ? f3 : f3 * s;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(f0, f1), h1v = __floats2bfloat162_rn(f2, f3);
+          const float f0 = __uint_as_float(v[4 * i]) + bv.x, f1 = __uint_as_float(v[4 * i + 1]) + bv.y;
+          const float f2 = __uint_as_float(v[4 * i + 2]) + bv.z, f3 = __uint_as_float(v[4 * i + 3]) + bv.w;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(f0, f0 * s), fmaxf(f1, f1 * s));
+          __nv_bfloat162 h1v = __floats2bfloat162_rn(fmaxf(f2, f2 * s), fmaxf(f3, f3 * s));
           pk[2 * i] = inside ? *reinterpret_cast<uint32_t*>(&h0) : 0u;
           pk[2 * i + 1] = inside ? *reinterpret_cast<uint32_t*>(&h1v) : 0u;
         }
-        // 32 channels = four 16-byte chunks of this row in panel (n0 / CH_PANEL)
+        // 16 channels = two 16-byte chunks of this row in panel (n0 / CH_PANEL)
         const int pn = n0 / CH_PANEL;
         const int chunk0 = (n0 % CH_PANEL) / 8;
         uint8_t* prow = mdst + pn * m_panel_bytes;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
           uint32_t off = static_cast<uint32_t>(r) * ROWB + (chunk0 + q) * 16;
           off ^= ((off >> 7) & SWZ) << 4;
           *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
@@ -317,130 +329,94 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
         mbar_arrive(&acc_empty[ln * 2 + 0]);
         mbar_arrive(&m_full[ln]);
       }
+#ifdef E2E_TRACE
+      if (threadIdx.x == 128 && blockIdx.x < 512) {
+        g_trace[blockIdx.x][2] += te1 - te0;           // epi1: waiting for the accumulator
+        g_trace[blockIdx.x][3] += gtime_ns() - te1;    // epi1: work
+      }
+#endif
+    };
+
+    // Residual of job c2(n): 16 bf16 of this thread's row per item, both items of the warp fetched one whole job
+    // early (before the c1 epilogue that precedes this c2 epilogue): the L2/HBM latency is off the critical path.
+    uint4 rqa[2], rqb[2];
+    auto item_off = [&](int n, int item, int& n0, bool& valid) -> size_t {
+      const int u = blockIdx.x + n * gridDim.x;
+      const int b = u / p.tiles_per_b;
+      const int t0 = (u - b * p.tiles_per_b) * p.r_out;
+      const int m = item / nchunk, cc = item - m * nchunk;
+      const int o = m * 128 + row_in_tile;
+      const int t = t0 + o;
+      valid = item < items && o < p.r_out && t < p.T;
+      n0 = cc * 16;
+      return (static_cast<size_t>(b) * p.T + (valid ? t : 0)) * p.nt + n0;
+    };
+    auto prefetch_res = [&](int n) {
+      int n0;
+      bool valid;
+      size_t off = item_off(n, part, n0, valid);
+      if (valid) ld_global_256(p.res_act + off, rqa[0], rqa[1]);
+      else rqa[0] = rqa[1] = make_uint4(0u, 0u, 0u, 0u);
+      off = item_off(n, part + 4, n0, valid);
+      if (valid) ld_global_256(p.res_act + off, rqb[0], rqb[1]);
+      else rqb[0] = rqb[1] = make_uint4(0u, 0u, 0u, 0u);
     };
 
     // c2 epilogue: acc + bias2 + residual (+ running sum, / divisor) -> global
     auto epi2 = [&](int n) {
-      const int u = blockIdx.x + n * gridDim.x;
-      const int b = u / p.tiles_per_b;
-      const int t0 = (u - b * p.tiles_per_b) * p.r_out;
       const int ln = n & 1;
       const uint32_t par = (n >> 1) & 1;
-      uint4 rqa[4], rqb[4];
-      auto prefetch = [&](int item, uint4 (&dst)[4]) {
-        const int m = item / nchunk, cc = item - m * nchunk;
-        const int o = m * 128 + row_in_tile;
-        const int t = t0 + o;
-        if (item < items && o < p.r_out && t < p.T) {
-          const uint4* src =
-              reinterpret_cast<const uint4*>(p.res_act + (static_cast<size_t>(b) * p.T + t) * p.nt + cc * 32);
-          ld_global_256(src, dst[0], dst[1]);
-          ld_global_256(src + 2, dst[2], dst[3]);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+      uint4 sqa[4], sqb[4];
+      int n0a, n0b;
+      bool va, vb;
+      const size_t offa = item_off(n, part, n0a, va), offb = item_off(n, part + 4, n0b, vb);
+      if (p.sum_in) {
+        if (va) {
+          ld_global_256(p.sum_in + offa, sqa[0], sqa[1]);
+          ld_global_256(p.sum_in + offa + 8, sqa[2], sqa[3]);
         }
-      };
-      uint4 sq[8];  // running-sum prefetch, one item ahead
-      auto prefetch_sum = [&](int item) {
-        const int m = item / nchunk, cc = item - m * nchunk;
-        const int o = m * 128 + row_in_tile;
-        const int t = t0 + o;
-        if (p.sum_in && item < items && o < p.r_out && t < p.T) {
-          const float* src = p.sum_in + (static_cast<size_t>(b) * p.T + t) * p.nt + cc * 32;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) ld_global_256(src + 8 * i, sq[2 * i], sq[2 * i + 1]);
+        if (vb) {
+          ld_global_256(p.sum_in + offb, sqb[0], sqb[1]);
+          ld_global_256(p.sum_in + offb + 8, sqb[2], sqb[3]);
         }
-      };
-      prefetch(half, rqa);
-      prefetch(half + 2, rqb);
-      prefetch_sum(half);
+      }
+#ifdef E2E_TRACE
+      const unsigned long long tf0 = gtime_ns();
+#endif
       mbar_wait(&acc_full[ln * 2 + 1], par, 0x700 + ln * 2);
       tc_fence_after_sync();
+#ifdef E2E_TRACE
+      const unsigned long long tf1 = gtime_ns();
+#endif
       const uint32_t d_tmem = tmem_base + (ln * 2 + 1) * acc_cols + lane_sel;
-      auto process = [&](int item, uint4 (&rq)[4]) {
-        const int m = item / nchunk, cc = item - m * nchunk;
-        const int o = m * 128 + row_in_tile;
-        const int t = t0 + o;
-        const bool valid = o < p.r_out && t < p.T;
-        uint32_t v[32];
-        tmem_ld_32x32(d_tmem + m * p.nt + cc * 32, v);
+      if (part < items) {
+        const int m = part / nchunk, cc = part - m * nchunk;
+        uint32_t v[16];
+        tmem_ld_32x16(d_tmem + m * p.nt + cc * 16, v);
         tmem_ld_wait();
-        float f[32];
-        const int n0 = cc * 32;
-        const float inv = p.res_inv_slope;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t w4[4] = {rq[i].x, rq[i].y, rq[i].z, rq[i].w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float lo = __uint_as_float(w4[j] << 16), hi = __uint_as_float(w4[j] & 0xffff0000u);
-            lo = lo > 0.f ? lo : lo * inv;
-            hi = hi > 0.f ? hi : hi * inv;
-            f[8 * i + 2 * j] = lo;
-            f[8 * i + 2 * j + 1] = hi;
-          }
-        }
-        prefetch(item + 4, rq);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias2 + n0) + i);
-          f[4 * i] += __uint_as_float(v[4 * i]) + bv.x;
-          f[4 * i + 1] += __uint_as_float(v[4 * i + 1]) + bv.y;
-          f[4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bv.z;
-          f[4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bv.w;
-        }
-        if (valid) {
-          const size_t off = (static_cast<size_t>(b) * p.T + t) * p.nt + n0;
-          if (p.sum_in) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              f[4 * i] += __uint_as_float(sq[i].x); f[4 * i + 1] += __uint_as_float(sq[i].y);
-              f[4 * i + 2] += __uint_as_float(sq[i].z); f[4 * i + 3] += __uint_as_float(sq[i].w);
-            }
-          }
-          prefetch_sum(item + 2);
-          if (p.divisor != 0.f) {
-            const float dv = p.divisor;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) f[i] = f[i] / dv;
-          }
-          if (p.out_f32) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              st_global_256(p.out_f32 + off + 8 * i,
-                            make_uint4(__float_as_uint(f[8 * i]), __float_as_uint(f[8 * i + 1]),
-                                       __float_as_uint(f[8 * i + 2]), __float_as_uint(f[8 * i + 3])),
-                            make_uint4(__float_as_uint(f[8 * i + 4]), __float_as_uint(f[8 * i + 5]),
-                                       __float_as_uint(f[8 * i + 6]), __float_as_uint(f[8 * i + 7])));
-          }
-          if (p.out_act) {
-            const float s = p.slope;
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float a = f[2 * i], c = f[2 * i + 1];
-              a = a > 0.f ? a : a * s;
-              c = c > 0.f ? c : c * s;
-              __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
-              pk[i] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            st_global_256(p.out_act + off, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
-            st_global_256(p.out_act + off + 16, make_uint4(pk[8], pk[9], pk[10], pk[11]),
-                          make_uint4(pk[12], pk[13], pk[14], pk[15]));
-          }
-        }
-      };
-      for (int item = half; item < items; item += 4) {
-        process(item, rqa);
-        if (item + 2 < items) process(item + 2, rqb);
+        epi_finish16(v, rqa, sqa, eo, n0a, offa, va);
+      }
+      if (part + 4 < items) {
+        const int item = part + 4;
+        const int m = item / nchunk, cc = item - m * nchunk;
+        uint32_t v[16];
+        tmem_ld_32x16(d_tmem + m * p.nt + cc * 16, v);
+        tmem_ld_wait();
+        epi_finish16(v, rqb, sqb, eo, n0b, offb, vb);
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ln * 2 + 1]);
+#ifdef E2E_TRACE
+      if (threadIdx.x == 128 && blockIdx.x < 512) {
+        g_trace[blockIdx.x][5] += tf1 - tf0;           // epi2: waiting for the accumulator
+        g_trace[blockIdx.x][6] += gtime_ns() - tf1;    // epi2: work
+      }
+#endif
     };
 
     for (int n = 0; n <= N; ++n) {
+      if (n >= 1) prefetch_res(n - 1);
       if (n < N) epi1(n);
       if (n >= 1) epi2(n - 1);
     }

@@ -254,11 +254,12 @@ int main(int argc, char** argv) {
     launch_pair(plan, 0);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpyFromSymbol(tr, g_trace, sizeof(tr)));
-    printf("  trace: cta | kernel us | MMA-thread waits (us): acc_empty m_full w_full a_full | units\n");
+    printf("  trace: cta | kernel us | MMA-thread waits (us): acc_empty m_full w_full a_full | units | epi warp4: epi1 wait/work, epi2 wait/work\n");
     for (int i = 0; i < (int)plan.grid.x && i < 512; i += 49) {
       const int nu = (p.n_units - i + plan.grid.x - 1) / plan.grid.x;
-      printf("  %5d | %8.2f | %8.2f %8.2f %8.2f %8.2f | %d\n", i, (tr[i][7] - tr[i][0]) * 1e-3, tr[i][8] * 1e-3,
-             tr[i][9] * 1e-3, tr[i][10] * 1e-3, tr[i][11] * 1e-3, nu);
+      printf("  %5d | %8.2f | %8.2f %8.2f %8.2f %8.2f | %d | %7.2f %7.2f %7.2f %7.2f\n", i, (tr[i][7] - tr[i][0]) * 1e-3,
+             tr[i][8] * 1e-3, tr[i][9] * 1e-3, tr[i][10] * 1e-3, tr[i][11] * 1e-3, nu, tr[i][2] * 1e-3, tr[i][3] * 1e-3,
+             tr[i][5] * 1e-3, tr[i][6] * 1e-3);
     }
   }
 #endif
