@@ -55,7 +55,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "selp.b32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity)  // (an explicit suspend-time hint was measured: 2 % slower, wake-up latency)
       : "memory");
   return ok != 0;
 }
