@@ -34,11 +34,69 @@ __global__ void mel_to_act_kernel(const float* __restrict__ mel, long long sB, l
 }
 
 constexpr int kPostMaxW = 7 * 64;
+constexpr int kPostTile = 512;  // output samples per block (2 per thread)
 
-// w: [k][C] fp32 (tap-major), one output channel.
+// w: [k][C] fp32 (tap-major), one output channel.  A block stages the bf16 rows [t0 - half, t0 + 512 + half) in
+// shared memory with coalesced 16-byte loads (rows outside the utterance = 0: conv_post's zero padding) and every
+// thread produces two adjacent samples, so each staged row is unpacked once for two outputs.
+template <int C, int K>
 __global__ void __launch_bounds__(256)
 post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, float bias, int B, int T,
-                      int C, int k, float* __restrict__ wav) {
+                      float* __restrict__ wav) {
+  constexpr int HALF = (K - 1) / 2;
+  constexpr int ROWS = kPostTile + 2 * HALF;
+  constexpr int ROW16 = C / 8;       // uint4 per row
+  constexpr int PITCH = ROW16 + 1;   // padded row pitch: adjacent threads read rows two apart -> 2-way conflicts at most
+  __shared__ float sw[K * C];
+  __shared__ uint4 rows[ROWS * PITCH];
+  for (int i = threadIdx.x; i < K * C; i += blockDim.x) sw[i] = w[i];
+  const int t0 = blockIdx.x * kPostTile;
+  const int b = blockIdx.y;
+  const uint4* src = reinterpret_cast<const uint4*>(act + (long long)b * T * C);
+  for (int i = threadIdx.x; i < ROWS * ROW16; i += blockDim.x) {
+    const int r = i / ROW16;
+    const int t = t0 - HALF + r;
+    rows[r * PITCH + (i - r * ROW16)] =
+        (t >= 0 && t < T) ? __ldg(src + (long long)t * ROW16 + (i - r * ROW16)) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  const int o = 2 * threadIdx.x;  // first of this thread's two outputs, relative to t0
+  float acc0 = bias, acc1 = bias;
+#pragma unroll
+  for (int j = 0; j <= K; ++j) {  // staged row o + j feeds output o with tap j and output o+1 with tap j-1
+    const uint4* row = rows + (o + j) * PITCH;
+#pragma unroll
+    for (int c8 = 0; c8 < ROW16; ++c8) {
+      const uint4 v = row[c8];
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float lo = __uint_as_float(u[i] << 16), hi = __uint_as_float(u[i] & 0xffff0000u);
+        if (j < K) {
+          acc0 = fmaf(lo, sw[j * C + c8 * 8 + 2 * i], acc0);
+          acc0 = fmaf(hi, sw[j * C + c8 * 8 + 2 * i + 1], acc0);
+        }
+        if (j > 0) {
+          acc1 = fmaf(lo, sw[(j - 1) * C + c8 * 8 + 2 * i], acc1);
+          acc1 = fmaf(hi, sw[(j - 1) * C + c8 * 8 + 2 * i + 1], acc1);
+        }
+      }
+    }
+  }
+  const int t = t0 + o;
+  float* dst = wav + (long long)b * T + t;
+  if (t + 1 < T && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    *reinterpret_cast<float2*>(dst) = make_float2(tanhf(acc0), tanhf(acc1));
+  } else {
+    if (t < T) dst[0] = tanhf(acc0);
+    if (t + 1 < T) dst[1] = tanhf(acc1);
+  }
+}
+
+// Generic fallback (any C multiple of 8, any odd k): one output per thread, rows read through L1.
+__global__ void __launch_bounds__(256)
+post_conv_tanh_generic_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, float bias, int B,
+                              int T, int C, int k, float* __restrict__ wav) {
   __shared__ float sw[kPostMaxW];
   for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -57,9 +115,8 @@ post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const float* __rest
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&u[i]);
-        acc = fmaf(__low2float(h), wj[c8 * 8 + 2 * i], acc);
-        acc = fmaf(__high2float(h), wj[c8 * 8 + 2 * i + 1], acc);
+        acc = fmaf(__uint_as_float(u[i] << 16), wj[c8 * 8 + 2 * i], acc);
+        acc = fmaf(__uint_as_float(u[i] & 0xffff0000u), wj[c8 * 8 + 2 * i + 1], acc);
       }
     }
   }

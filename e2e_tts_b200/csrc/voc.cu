@@ -37,12 +37,10 @@ struct Op {
 struct PlanKey {
   int B, T;
   const void* ws;
-  const void* wav;
   bool operator<(const PlanKey& o) const {
     if (B != o.B) return B < o.B;
     if (T != o.T) return T < o.T;
-    if (ws != o.ws) return ws < o.ws;
-    return wav < o.wav;
+    return ws < o.ws;
   }
 };
 
@@ -502,7 +500,7 @@ extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t
   if (workspace_bytes < e2e_voc_workspace_bytes(v, B, T)) return fail(-1, "workspace too small");
   if ((long long)T * v->hop > 0x7fffffffLL) return fail(-1, "utterance too long");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  PlanKey key{B, T, workspace, wav};
+  PlanKey key{B, T, workspace};
   auto it = v->plans.find(key);
   if (it == v->plans.end()) {
     std::vector<Op> ops;
@@ -536,9 +534,15 @@ extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t
     } else {
       const Layer& L = v->layers[op.layer];
       const int Tout = T * v->hop;
-      dim3 grid((Tout + 255) / 256, B);
-      post_conv_tanh_kernel<<<grid, 256, 0, st>>>(bf.Y, reinterpret_cast<const float*>(L.d_w), L.post_bias, B, Tout,
-                                                  L.cin, L.k, wav);
+      if (L.cin == 32 && L.k == 7) {
+        dim3 grid((Tout + kPostTile - 1) / kPostTile, B);
+        post_conv_tanh_kernel<32, 7><<<grid, 256, 0, st>>>(bf.Y, reinterpret_cast<const float*>(L.d_w), L.post_bias, B,
+                                                           Tout, wav);
+      } else {
+        dim3 grid((Tout + 255) / 256, B);
+        post_conv_tanh_generic_kernel<<<grid, 256, 0, st>>>(bf.Y, reinterpret_cast<const float*>(L.d_w), L.post_bias,
+                                                            B, Tout, L.cin, L.k, wav);
+      }
     }
     if (oi == last_conv && v->ev_end) cudaEventRecord(v->ev_end, st);
   }
