@@ -63,14 +63,15 @@ struct ConvParams {
   const __nv_bfloat16* res_act;  // bf16 [B][T][n_total] = leaky_relu(x, 1/res_inv_slope) of the residual x of
                                  // `xt + x` (layers.py:39), or nullptr; x is recovered by the inverse LeakyReLU
   float res_inv_slope;  // 1 / slope used when res_act was written (10 for LRELU_SLOPE = 0.1)
-  const float* sum_in;  // fp32 running sum over resblocks (generator.py:44-47) or nullptr
+  const __nv_bfloat16* sum_a;  // bf16 [B][T][n_total] running sum over the stage's resblocks (generator.py:44-47), or
+                               // nullptr
   float* out_f32;       // fp32 [B][T][n_total] or nullptr
   __nv_bfloat16* out_act;  // bf16 [B][T][n_total] = leaky_relu(out, slope) or nullptr
 };
 
 #ifdef E2E_TRACE
 // Debug build only: per-CTA phase timestamps (globaltimer ns), read back by tests/cuda.
-__device__ unsigned long long g_trace[512][12];
+__device__ unsigned long long g_trace[512][16];  // [12], [13]: clock64 at kernel start / end
 __device__ __forceinline__ unsigned long long gtime_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -78,7 +79,11 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 }
 #define E2E_TR(slot)                                                     \
   do {                                                                   \
-    if (blockIdx.x < 512) g_trace[blockIdx.x][slot] = gtime_ns();        \
+    if (blockIdx.x < 512) {                                              \
+      g_trace[blockIdx.x][slot] = gtime_ns();                            \
+      if ((slot) == 0) g_trace[blockIdx.x][12] = clock64();              \
+      if ((slot) == 7) g_trace[blockIdx.x][13] = clock64();              \
+    }                                                                    \
   } while (0)
 #else
 #define E2E_TR(slot)
@@ -148,10 +153,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
       constexpr int ch_per_panel = ROWB / 2;
       const int boxes = p.slab_rows / p.box_rows;
       uint32_t slot = 0, par = 1;  // ring position; `par` is the parity a fresh/recycled slot is waited on
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const int tb = u / p.n_tiles;
-        const int b = tb / p.tiles_per_b;
-        const int t0 = (tb - b * p.tiles_per_b) * (128 * MT);
+      UnitIter it;
+      it.init(blockIdx.x, gridDim.x, p.n_tiles, p.tiles_per_b);
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it.next()) {
+        const int b = it.b;
+        const int t0 = it.tile * (128 * MT);
         for (int pn = 0; pn < p.panels; ++pn) {
           mbar_wait(&panel_empty[slot], par, 0x100 + slot);
           mbar_arrive_expect_tx(&panel_full[slot], panel_bytes);
@@ -170,8 +176,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
     if (lane == 0) {
       // ---------------- weight producer (bulk copies) ----------------
       uint32_t stage = 0, par = 1;
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const int nti = u % p.n_tiles;
+      UnitIter it;
+      it.init(blockIdx.x, gridDim.x, p.n_tiles, p.tiles_per_b);
+      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it.next()) {
+        const int nti = it.nti;
         const uint8_t* wsrc = p.w + static_cast<size_t>(nti) * total_tiles * tile_bytes;
         int first = 0;
         for (int c = 0; c < p.n_chunks; ++c, first += p.tiles_per_chunk) {
@@ -199,8 +207,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
     const uint32_t panel16 = panel_bytes >> 4, stage16 = p.stage_bytes >> 4, tile16 = tile_bytes >> 4;
     uint32_t slot = 0, ppar = 0, stage = 0, wpar = 0, acc = 0, apar = 1;
     bool first_unit = true;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int nti = u % p.n_tiles;
+    UnitIter uit;
+    uit.init(blockIdx.x, gridDim.x, p.n_tiles, p.tiles_per_b);
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, uit.next()) {
+      const int nti = uit.nti;
       mbar_wait(&acc_empty[acc], apar, 0x300 + acc);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * (MT * p.nt);
@@ -267,23 +277,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
     const int items = MT * nchunk;  // (m tile, 16-column chunk) pairs
     const int row_in_tile = quarter * 32 + lane;
     EpiOut eo;
-    eo.bias = p.bias;
-    eo.sum_in = p.sum_in;
+    eo.sum_a = p.sum_a;
     eo.out_f32 = p.out_f32;
     eo.out_act = p.out_act;
     eo.slope = p.slope;
-    eo.divisor = p.divisor;
+    eo.scale = p.divisor != 0.f ? 1.0f / p.divisor : 0.f;
     eo.inv = p.res_inv_slope;
     uint32_t it = 0, acc = 0, apar = 0;
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it) {
-      const int nti = u % p.n_tiles;
-      const int tb = u / p.n_tiles;
-      const int b = tb / p.tiles_per_b;
-      const int t0 = (tb - b * p.tiles_per_b) * (128 * MT);
+    UnitIter uit;
+    uit.init(blockIdx.x, gridDim.x, p.n_tiles, p.tiles_per_b);
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it, uit.next()) {
+      const int nti = uit.nti;
+      const int b = uit.b;
+      const int t0 = uit.tile * (128 * MT);
       const uint32_t d_tmem = tmem_base + acc * (MT * p.nt) + (static_cast<uint32_t>(quarter * 32) << 16);
 
-      // residual (16 bf16) two items ahead, running sum (16 fp32) one item ahead
-      uint4 rqa[2], rqb[2], sq[4];
+      // residual and partial sums (16 bf16 each) are fetched one item ahead, before the accumulator is waited on
+      uint4 rqa[2], rqb[2], saa[2], sab[2];
       auto item_off = [&](int item, int& n0, bool& valid) -> size_t {
         const int m = item / nchunk, cc = item - m * nchunk;
         const int t = t0 + m * 128 + row_in_tile;
@@ -291,47 +301,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
         n0 = nti * p.nt + cc * 16;
         return (static_cast<size_t>(b) * p.T + (valid ? t : 0)) * p.n_total + n0;
       };
-      auto prefetch = [&](int item, uint4 (&dst)[2]) {
+      auto prefetch = [&](int item, uint4 (&rq)[2], uint4 (&sa)[2]) {
         int n0;
         bool valid;
         const size_t off = item_off(item, n0, valid);
-        if (p.res_act && valid) {
-          ld_global_256(p.res_act + off, dst[0], dst[1]);  // plain loads: the buffer may be updated in place
-        } else {
-          dst[0] = dst[1] = make_uint4(0u, 0u, 0u, 0u);
+        rq[0] = rq[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) {
+          if (p.res_act) ld_global_256(p.res_act + off, rq[0], rq[1]);  // plain loads: may be updated in place
+          if (p.sum_a) ld_global_256(p.sum_a + off, sa[0], sa[1]);
         }
       };
-      auto prefetch_sum = [&](int item) {
-        int n0;
-        bool valid;
-        const size_t off = item_off(item, n0, valid);
-        if (p.sum_in && valid) {
-          ld_global_256(p.sum_in + off, sq[0], sq[1]);
-          ld_global_256(p.sum_in + off + 8, sq[2], sq[3]);
-        }
-      };
-      prefetch(part, rqa);  // overlaps the MMAs of this unit
-      prefetch(part + 4, rqb);
-      prefetch_sum(part);
+      prefetch(part, rqa, saa);  // overlaps the MMAs of this unit
+      prefetch(part + 4, rqb, sab);
       mbar_wait(&acc_full[acc], apar, 0x600 + acc);
       tc_fence_after_sync();
       if (it == 0 && threadIdx.x == 128) E2E_TR(5);
 
-      auto process = [&](int item, uint4 (&rq)[2]) {
+      auto process = [&](int item, uint4 (&rq)[2], uint4 (&sa)[2]) {
         const int m = item / nchunk, cc = item - m * nchunk;
         int n0;
         bool valid;
         const size_t off = item_off(item, n0, valid);
         uint32_t v[16];
         tmem_ld_32x16(d_tmem + m * p.nt + cc * 16, v);
+        float4 bv[4];  // the bias loads are in flight together with the TMEM load
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
         tmem_ld_wait();
-        epi_finish16(v, rq, sq, eo, n0, off, valid);
-        prefetch(item + 8, rq);   // refill this slot for the item after next
-        prefetch_sum(item + 4);   // (sq was consumed above)
+        epi_finish16(v, bv, rq, sa, eo, off, valid);
+        prefetch(item + 8, rq, sa);  // refill this slot for the item after next
       };
       for (int item = part; item < items; item += 8) {
-        process(item, rqa);
-        if (item + 4 < items) process(item + 4, rqb);
+        process(item, rqa, saa);
+        if (item + 4 < items) process(item + 4, rqb, sab);
       }
       // all of this warp's TMEM reads of the unit are complete (tcgen05.wait::ld above): release the accumulator
       tc_fence_before_sync();

@@ -2,9 +2,9 @@
 // one accumulator row: the thread that owns TMEM lane r reads them with one tcgen05.ld.32x32b.x16, and all global
 // traffic of the item is 32-byte aligned 256-bit accesses (one full sector per lane and instruction):
 //   residual  16 bf16 = 32 B   (leaky_relu(x) of the pair's input; x recovered by the inverse LeakyReLU)
-//   sum_in    16 fp32 = 64 B   (running resblock sum, generator.py:44-47)
+//   sum_a     16 bf16 = 32 B   (running sum over the resblocks of the stage, generator.py:44-47)
 //   out_f32   16 fp32 = 64 B
-//   out_act   16 bf16 = 32 B   (leaky_relu(result, slope))
+//   out_act   16 bf16 = 32 B   (leaky_relu(result, slope); slope 1 stores the plain result)
 #pragma once
 #include "ptx.cuh"
 
@@ -13,7 +13,7 @@ namespace e2e {
 constexpr int kEpiWarps = 16;                      // four warps per TMEM lane quarter
 constexpr int kConvThreads = (4 + kEpiWarps) * 32;  // + TMA producer, weight producer, MMA issuer, TMEM allocator
 
-// TMEM -> registers: 16 consecutive fp32 columns of this thread's lane.
+// TMEM -> registers: 16 consecutive fp32 columns of this thread's lane (asynchronous until tmem_ld_wait()).
 __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -24,22 +24,66 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "memory");
 }
 
-struct EpiOut {
-  const float* bias;    // + column offset already applied by the caller? no: base pointer, column added here
-  const float* sum_in;  // base pointers (nullptr = absent)
-  float* out_f32;
-  __nv_bfloat16* out_act;
-  float slope, divisor, inv;
+// Persistent-grid work iterator: unit u = (b * tiles_per_b + tile) * n_tiles + nti, visited with stride `step`.
+// The decomposition is carried incrementally (four integer divisions per thread and kernel instead of several
+// per unit and epilogue call).
+struct UnitIter {
+  int nti, tile, b;
+  int s_nti, s_tile, s_b;
+  int n_tiles, tiles_per_b;
+  __device__ __forceinline__ void init(int u0, int step, int n_tiles_, int tiles_per_b_) {
+    n_tiles = n_tiles_;
+    tiles_per_b = tiles_per_b_;
+    nti = u0 % n_tiles;
+    int tb = u0 / n_tiles;
+    b = tb / tiles_per_b;
+    tile = tb - b * tiles_per_b;
+    s_nti = step % n_tiles;
+    tb = step / n_tiles;
+    s_b = tb / tiles_per_b;
+    s_tile = tb - s_b * tiles_per_b;
+  }
+  __device__ __forceinline__ void next() {
+    nti += s_nti;
+    int carry = 0;
+    if (nti >= n_tiles) {
+      nti -= n_tiles;
+      carry = 1;
+    }
+    tile += s_tile + carry;
+    b += s_b;
+    if (tile >= tiles_per_b) {
+      tile -= tiles_per_b;
+      ++b;
+    }
+  }
 };
 
-// acc (+ bias) + residual (+ sum) (/ divisor) -> out_f32 and/or leaky_relu -> out_act, for one 16-column item.
+struct EpiOut {
+  const __nv_bfloat16* sum_a;  // bf16 running resblock sum to add (nullptr = absent)
+  float* out_f32;
+  __nv_bfloat16* out_act;
+  float slope, scale, inv;  // scale: 0 = none, else result *= scale (1 / num_kernels)
+};
+
+__device__ __forceinline__ void add_bf16x16(float (&f)[16], const uint4 (&q)[2]) {
+  const uint32_t w[8] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    f[2 * j] += __uint_as_float(w[j] << 16);
+    f[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+
+// acc + bias + residual (+ partial sums) (* scale) -> out_f32 and/or leaky_relu -> out_act, for one 16-column item.
 //   v        raw accumulator bits
+//   bv       bias of the 16 columns
 //   rq       residual: 16 bf16 (zeros when there is none)
-//   sq       running sum: 16 fp32 (only read when o.sum_in != nullptr)
-//   n0       first output column of the item (bias index)
-//   off      element offset of (row, n0) in the [B][T][n_total] outputs
-__device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const uint4 (&rq)[2], const uint4 (&sq)[4],
-                                             const EpiOut& o, int n0, size_t off, bool valid) {
+//   sa       running sum: 16 bf16 (only read when o.sum_a != nullptr)
+//   off      element offset of (row, first column) in the [B][T][n_total] outputs
+__device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const float4 (&bv)[4], const uint4 (&rq)[2],
+                                             const uint4 (&sa)[2], const EpiOut& o, size_t off, bool valid) {
+  if (!valid) return;
   float f[16];
   const uint32_t w[8] = {rq[0].x, rq[0].y, rq[0].z, rq[0].w, rq[1].x, rq[1].y, rq[1].z, rq[1].w};
 #pragma unroll
@@ -51,26 +95,16 @@ __device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const uint
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(o.bias + n0) + i);
-    f[4 * i] += __uint_as_float(v[4 * i]) + bv.x;
-    f[4 * i + 1] += __uint_as_float(v[4 * i + 1]) + bv.y;
-    f[4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bv.z;
-    f[4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bv.w;
+    f[4 * i] += __uint_as_float(v[4 * i]) + bv[i].x;
+    f[4 * i + 1] += __uint_as_float(v[4 * i + 1]) + bv[i].y;
+    f[4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bv[i].z;
+    f[4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bv[i].w;
   }
-  if (!valid) return;
-  if (o.sum_in) {
+  if (o.sum_a) add_bf16x16(f, sa);
+  if (o.scale != 0.f) {
+    const float sc = o.scale;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      f[4 * i] += __uint_as_float(sq[i].x);
-      f[4 * i + 1] += __uint_as_float(sq[i].y);
-      f[4 * i + 2] += __uint_as_float(sq[i].z);
-      f[4 * i + 3] += __uint_as_float(sq[i].w);
-    }
-  }
-  if (o.divisor != 0.f) {
-    const float dv = o.divisor;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = f[i] / dv;  // true division, like `xs / self.num_kernels`
+    for (int i = 0; i < 16; ++i) f[i] *= sc;
   }
   if (o.out_f32) {
 #pragma unroll
@@ -87,7 +121,7 @@ __device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const uint
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float a = f[2 * i], c = f[2 * i + 1];
-      __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, a * s), fmaxf(c, c * s));  // leaky_relu, 0 < s < 1
+      __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, a * s), fmaxf(c, c * s));  // leaky_relu, 0 < s <= 1
       pk[i] = *reinterpret_cast<uint32_t*>(&h);
     }
     st_global_256(o.out_act + off, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));

@@ -19,6 +19,8 @@ inline bool pair_supported(int C, int k, int d) {
   return (C == 32 || C == 64 || C == 128) && (k & 1) && k <= kMaxTaps && (k - 1) * d <= 120;
 }
 
+constexpr int kPairTailBytes = 512 + 1024;  // mbarriers + the two staged bias vectors
+
 inline int plan_pair(PairPlan& plan, int C, int k, int d, int B, int T, int n_sms = 148) {
   if (!pair_supported(C, k, d)) return fail(-2, "fused pair: unsupported channel count / kernel size");
   PairParams& p = plan.p;
@@ -36,7 +38,7 @@ inline int plan_pair(PairPlan& plan, int C, int k, int d, int B, int T, int n_sm
   const int need = 128 * mt + (k - 1) * d;
   const int tile_bytes = C * rowb;
   const int total_tiles = p.panels * k;
-  const int budget = kSmemLimit - 1024 - 512;
+  const int budget = kSmemLimit - 1024 - kPairTailBytes;
   for (int box = 128; box >= 16; box >>= 1) {
     const int rows = (need + box - 1) / box * box;
     if (rows - need > 32 && box > 16) continue;
@@ -55,7 +57,7 @@ inline int plan_pair(PairPlan& plan, int C, int k, int d, int B, int T, int n_sm
       p.stage_bytes = stage_bytes;
       p.tiles_per_b = (T + p.r_out - 1) / p.r_out;
       p.n_units = B * p.tiles_per_b;
-      plan.smem_bytes = 1024 + slabs + stages * stage_bytes + 512;
+      plan.smem_bytes = 1024 + slabs + stages * stage_bytes + kPairTailBytes;
       plan.grid = dim3(p.n_units < n_sms ? p.n_units : n_sms, 1, 1);
       return 0;
     }

@@ -44,7 +44,7 @@ struct PairParams {
   const float* bias1;
   const float* bias2;
   const __nv_bfloat16* res_act;  // == the kernel's input tensor (bf16 leaky_relu(x)), read for the residual
-  const float* sum_in;
+  const __nv_bfloat16* sum_a;    // bf16 running sum over the stage's resblocks (generator.py:44-47) or nullptr
   float* out_f32;
   __nv_bfloat16* out_act;
 };
@@ -84,6 +84,8 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
   uint64_t* acc_empty = acc_full + 4;         // [2][2]
   uint64_t* m_full = acc_empty + 4;           // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(m_full + 2);
+  float* s_bias1 = reinterpret_cast<float*>(bars + 64);  // [nt] biases of c1 / c2, staged once (512 B past `bars`)
+  float* s_bias2 = s_bias1 + 128;
 
   // units of this CTA: u_n = blockIdx.x + n * gridDim.x, n = 0 .. N-1
   const int N = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -116,6 +118,10 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  for (int i = threadIdx.x; i < p.nt; i += blockDim.x) {
+    s_bias1[i] = p.bias1[i];
+    s_bias2[i] = p.bias2[i];
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -126,10 +132,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
     if (lane == 0) {
       // ---------------- input slab producer (TMA) ----------------
       const int boxes = p.a_rows / p.box_rows;
-      for (int n = 0; n < N; ++n) {
-        const int u = blockIdx.x + n * gridDim.x;
-        const int b = u / p.tiles_per_b;
-        const int t0 = (u - b * p.tiles_per_b) * p.r_out;
+      UnitIter uit;
+      uit.init(blockIdx.x, gridDim.x, 1, p.tiles_per_b);
+      for (int n = 0; n < N; ++n, uit.next()) {
+        const int b = uit.b;
+        const int t0 = uit.tile * p.r_out;
         const int ln = n & 1;
         const uint32_t par = ((n >> 1) & 1) ^ 1;
         for (int pn = 0; pn < p.panels; ++pn) {
@@ -259,25 +266,58 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
     // ---------------- epilogue ----------------
     const int e = warp - 4;
     const int quarter = e & 3;
-    const int part = e >> 2;        // this warp takes the items with item % 4 == part
+    const int part = e >> 2;
     const int nchunk = p.nt >> 4;
-    const int items = MT * nchunk;  // == 8 for every supported (C, MT): exactly two items per warp
+    // MT * nchunk == 8 items per job for every supported (C, MT): this warp owns items `part` and `part + 4`,
+    // i.e. fixed (m tile, 16-column chunk) pairs for the whole kernel
+    const int mA = part / nchunk, ccA = part - mA * nchunk;
+    const int mB = (part + 4) / nchunk, ccB = (part + 4) - mB * nchunk;
     const int row_in_tile = quarter * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     EpiOut eo;
-    eo.bias = p.bias2;
-    eo.sum_in = p.sum_in;
+    eo.sum_a = p.sum_a;
     eo.out_f32 = p.out_f32;
     eo.out_act = p.out_act;
     eo.slope = p.slope;
-    eo.divisor = p.divisor;
+    eo.scale = p.divisor != 0.f ? 1.0f / p.divisor : 0.f;
     eo.inv = p.res_inv_slope;
+    const float smid = p.slope_mid;
 
-    // c1 epilogue: acc -> +bias1 -> leaky_relu -> bf16 -> M slab (zero outside the utterance)
-    auto epi1 = [&](int n) {
-      const int u = blockIdx.x + n * gridDim.x;
-      const int b = u / p.tiles_per_b;
-      const int t0 = (u - b * p.tiles_per_b) * p.r_out;
+    // one 16-column item of c1: acc + bias1 -> leaky_relu -> bf16 -> M slab (zero outside the utterance)
+    auto store_mid = [&](const uint32_t (&v)[16], const float4 (&bv)[4], int m, int cc, int t0, uint8_t* mdst) {
+      const int r = m * 128 + row_in_tile;   // M slab row
+      const int t = t0 - h2 + r;             // global time step of this row
+      const bool inside = t >= 0 && t < p.T;
+      uint32_t pk[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float f0 = __uint_as_float(v[4 * i]) + bv[i].x, f1 = __uint_as_float(v[4 * i + 1]) + bv[i].y;
+        const float f2 = __uint_as_float(v[4 * i + 2]) + bv[i].z, f3 = __uint_as_float(v[4 * i + 3]) + bv[i].w;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(f0, f0 * smid), fmaxf(f1, f1 * smid));
+        __nv_bfloat162 h1v = __floats2bfloat162_rn(fmaxf(f2, f2 * smid), fmaxf(f3, f3 * smid));
+        pk[2 * i] = inside ? *reinterpret_cast<uint32_t*>(&h0) : 0u;
+        pk[2 * i + 1] = inside ? *reinterpret_cast<uint32_t*>(&h1v) : 0u;
+      }
+      // 16 channels = two 16-byte chunks of this row in panel (n0 / CH_PANEL)
+      const int n0 = cc * 16;
+      const int pn = n0 / CH_PANEL;
+      const int chunk0 = (n0 % CH_PANEL) / 8;
+      uint8_t* prow = mdst + pn * m_panel_bytes;
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t off = static_cast<uint32_t>(r) * ROWB + (chunk0 + q) * 16;
+        off ^= ((off >> 7) & SWZ) << 4;
+        *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      }
+    };
+    auto lds_bias = [&](const float* sb, int cc, float4 (&bv)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) bv[i] = *reinterpret_cast<const float4*>(sb + cc * 16 + 4 * i);
+    };
+
+    // c1 epilogue.  The TMEM load of the second item is in flight while the first item is processed; the bias
+    // comes from shared memory while the TMEM loads are in flight.
+    auto epi1 = [&](int n, int t0) {
       const int ln = n & 1;
       const uint32_t par = (n >> 1) & 1;
       uint8_t* mdst = m_slab + ln * m_lane_bytes;
@@ -290,38 +330,16 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
       const unsigned long long te1 = gtime_ns();
 #endif
       const uint32_t d_tmem = tmem_base + (ln * 2 + 0) * acc_cols + lane_sel;
-      for (int item = part; item < items; item += 4) {
-        const int m = item / nchunk, cc = item - m * nchunk;
-        const int r = m * 128 + row_in_tile;   // M slab row
-        const int t = t0 - h2 + r;             // global time step of this row
-        const bool inside = t >= 0 && t < p.T;
-        uint32_t v[16];
-        tmem_ld_32x16(d_tmem + m * p.nt + cc * 16, v);
-        tmem_ld_wait();
-        const int n0 = cc * 16;
-        const float s = p.slope_mid;
-        uint32_t pk[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias1 + n0) + i);
-          const float f0 = __uint_as_float(v[4 * i]) + bv.x, f1 = __uint_as_float(v[4 * i + 1]) + bv.y;
-          const float f2 = __uint_as_float(v[4 * i + 2]) + bv.z, f3 = __uint_as_float(v[4 * i + 3]) + bv.w;
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(f0, f0 * s), fmaxf(f1, f1 * s));
-          __nv_bfloat162 h1v = __floats2bfloat162_rn(fmaxf(f2, f2 * s), fmaxf(f3, f3 * s));
-          pk[2 * i] = inside ? *reinterpret_cast<uint32_t*>(&h0) : 0u;
-          pk[2 * i + 1] = inside ? *reinterpret_cast<uint32_t*>(&h1v) : 0u;
-        }
-        // 16 channels = two 16-byte chunks of this row in panel (n0 / CH_PANEL)
-        const int pn = n0 / CH_PANEL;
-        const int chunk0 = (n0 % CH_PANEL) / 8;
-        uint8_t* prow = mdst + pn * m_panel_bytes;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          uint32_t off = static_cast<uint32_t>(r) * ROWB + (chunk0 + q) * 16;
-          off ^= ((off >> 7) & SWZ) << 4;
-          *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
-      }
+      uint32_t vA[16], vB[16];
+      float4 bv[4];
+      tmem_ld_32x16(d_tmem + mA * p.nt + ccA * 16, vA);
+      lds_bias(s_bias1, ccA, bv);
+      tmem_ld_wait();
+      tmem_ld_32x16(d_tmem + mB * p.nt + ccB * 16, vB);
+      store_mid(vA, bv, mA, ccA, t0, mdst);
+      lds_bias(s_bias1, ccB, bv);
+      tmem_ld_wait();
+      store_mid(vB, bv, mB, ccB, t0, mdst);
       tc_fence_before_sync();
       fence_proxy_async_smem();  // the M slab is read by the tensor core through the async proxy
       __syncwarp();
@@ -337,49 +355,33 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
 #endif
     };
 
-    // Residual of job c2(n): 16 bf16 of this thread's row per item, both items of the warp fetched one whole job
-    // early (before the c1 epilogue that precedes this c2 epilogue): the L2/HBM latency is off the critical path.
-    uint4 rqa[2], rqb[2];
-    auto item_off = [&](int n, int item, int& n0, bool& valid) -> size_t {
-      const int u = blockIdx.x + n * gridDim.x;
-      const int b = u / p.tiles_per_b;
-      const int t0 = (u - b * p.tiles_per_b) * p.r_out;
-      const int m = item / nchunk, cc = item - m * nchunk;
-      const int o = m * 128 + row_in_tile;
-      const int t = t0 + o;
-      valid = item < items && o < p.r_out && t < p.T;
-      n0 = cc * 16;
-      return (static_cast<size_t>(b) * p.T + (valid ? t : 0)) * p.nt + n0;
-    };
-    auto prefetch_res = [&](int n) {
-      int n0;
-      bool valid;
-      size_t off = item_off(n, part, n0, valid);
-      if (valid) ld_global_256(p.res_act + off, rqa[0], rqa[1]);
-      else rqa[0] = rqa[1] = make_uint4(0u, 0u, 0u, 0u);
-      off = item_off(n, part + 4, n0, valid);
-      if (valid) ld_global_256(p.res_act + off, rqb[0], rqb[1]);
-      else rqb[0] = rqb[1] = make_uint4(0u, 0u, 0u, 0u);
+    // Residual and running sum of job c2(n): 16 bf16 of this thread's row per item, both items of the warp fetched
+    // one whole job early (before the c1 epilogue that precedes this c2 epilogue): the L2/HBM latency is off the
+    // critical path.
+    uint4 rqa[2], rqb[2], sqa[2], sqb[2];
+    size_t offa = 0, offb = 0;
+    bool va = false, vb = false;
+    auto prefetch_res = [&](int b, int t0) {
+      const int oa = mA * 128 + row_in_tile, ob = mB * 128 + row_in_tile;
+      va = oa < p.r_out && t0 + oa < p.T;
+      vb = ob < p.r_out && t0 + ob < p.T;
+      offa = (static_cast<size_t>(b) * p.T + (va ? t0 + oa : 0)) * p.nt + ccA * 16;
+      offb = (static_cast<size_t>(b) * p.T + (vb ? t0 + ob : 0)) * p.nt + ccB * 16;
+      rqa[0] = rqa[1] = rqb[0] = rqb[1] = make_uint4(0u, 0u, 0u, 0u);
+      if (va) {
+        ld_global_256(p.res_act + offa, rqa[0], rqa[1]);
+        if (p.sum_a) ld_global_256(p.sum_a + offa, sqa[0], sqa[1]);
+      }
+      if (vb) {
+        ld_global_256(p.res_act + offb, rqb[0], rqb[1]);
+        if (p.sum_a) ld_global_256(p.sum_a + offb, sqb[0], sqb[1]);
+      }
     };
 
-    // c2 epilogue: acc + bias2 + residual (+ running sum, / divisor) -> global
+    // c2 epilogue: acc + bias2 + residual (+ running sum, * 1/divisor) -> global
     auto epi2 = [&](int n) {
       const int ln = n & 1;
       const uint32_t par = (n >> 1) & 1;
-      uint4 sqa[4], sqb[4];
-      int n0a, n0b;
-      bool va, vb;
-      const size_t offa = item_off(n, part, n0a, va), offb = item_off(n, part + 4, n0b, vb);
-      if (p.sum_in) {
-        if (va) {
-          ld_global_256(p.sum_in + offa, sqa[0], sqa[1]);
-          ld_global_256(p.sum_in + offa + 8, sqa[2], sqa[3]);
-        }
-        if (vb) {
-          ld_global_256(p.sum_in + offb, sqb[0], sqb[1]);
-          ld_global_256(p.sum_in + offb + 8, sqb[2], sqb[3]);
-        }
-      }
 #ifdef E2E_TRACE
       const unsigned long long tf0 = gtime_ns();
 #endif
@@ -389,24 +391,20 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
       const unsigned long long tf1 = gtime_ns();
 #endif
       const uint32_t d_tmem = tmem_base + (ln * 2 + 1) * acc_cols + lane_sel;
-      if (part < items) {
-        const int m = part / nchunk, cc = part - m * nchunk;
-        uint32_t v[16];
-        tmem_ld_32x16(d_tmem + m * p.nt + cc * 16, v);
-        tmem_ld_wait();
-        epi_finish16(v, rqa, sqa, eo, n0a, offa, va);
-      }
-      if (part + 4 < items) {
-        const int item = part + 4;
-        const int m = item / nchunk, cc = item - m * nchunk;
-        uint32_t v[16];
-        tmem_ld_32x16(d_tmem + m * p.nt + cc * 16, v);
-        tmem_ld_wait();
-        epi_finish16(v, rqb, sqb, eo, n0b, offb, vb);
-      }
+      uint32_t vA[16], vB[16];
+      float4 bv[4];
+      tmem_ld_32x16(d_tmem + mA * p.nt + ccA * 16, vA);
+      lds_bias(s_bias2, ccA, bv);
+      tmem_ld_wait();
+      tmem_ld_32x16(d_tmem + mB * p.nt + ccB * 16, vB);
+      epi_finish16(vA, bv, rqa, sqa, eo, offa, va);
+      lds_bias(s_bias2, ccB, bv);
+      tmem_ld_wait();
+      // every TMEM read of this warp has completed: release the accumulator before the global stores of item B
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ln * 2 + 1]);
+      epi_finish16(vB, bv, rqb, sqb, eo, offb, vb);
 #ifdef E2E_TRACE
       if (threadIdx.x == 128 && blockIdx.x < 512) {
         g_trace[blockIdx.x][5] += tf1 - tf0;           // epi2: waiting for the accumulator
@@ -415,10 +413,17 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
 #endif
     };
 
+    UnitIter uit;
+    uit.init(blockIdx.x, gridDim.x, 1, p.tiles_per_b);
+    int pb = 0, pt0 = 0;  // unit n - 1
     for (int n = 0; n <= N; ++n) {
-      if (n >= 1) prefetch_res(n - 1);
-      if (n < N) epi1(n);
+      if (n >= 1) prefetch_res(pb, pt0);
+      const int t0 = uit.tile * p.r_out;
+      if (n < N) epi1(n, t0);
       if (n >= 1) epi2(n - 1);
+      pb = uit.b;
+      pt0 = t0;
+      uit.next();
     }
   }
 

@@ -45,10 +45,10 @@ struct PlanKey {
 };
 
 // Activations live in HBM ONCE, as bf16 leaky_relu(x): that tensor is both the next convolution's operand and
-// (through the inverse LeakyReLU) the residual x of `xt + x`.  Only the running resblock sum is fp32.
+// (through the inverse LeakyReLU) the residual x of `xt + x`.  The running resblock sum `xs` (generator.py:44-47)
+// ping-pongs between two bf16 buffers.
 struct Buffers {
-  __nv_bfloat16 *melA, *preA, *A0, *A1, *M, *Y;
-  float* SUM;
+  __nv_bfloat16 *melA, *preA, *A0, *A1, *M, *Y, *S0, *S1;
   size_t total;
 };
 
@@ -309,7 +309,8 @@ static void carve(const e2e_voc* v, int B, int T, void* ws, Buffers& b) {
   b.A1 = (__nv_bfloat16*)take(E * 2);
   b.M = (__nv_bfloat16*)take(E * 2);
   b.Y = (__nv_bfloat16*)take(E * 2);
-  b.SUM = (float*)take(E * 4);
+  b.S0 = (__nv_bfloat16*)take(E * 2);
+  b.S1 = (__nv_bfloat16*)take(E * 2);
   b.total = off;
 }
 
@@ -322,7 +323,7 @@ extern "C" size_t e2e_voc_workspace_bytes(const e2e_voc* v, int32_t B, int32_t T
 
 // One conv launch: input activation `in` ([B][T][cin] bf16), outputs as requested.
 static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int T, const __nv_bfloat16* in,
-                        const __nv_bfloat16* res_act, const float* sum_in, float* out_f32, __nv_bfloat16* out_act,
+                        const __nv_bfloat16* res_act, const __nv_bfloat16* sum_a, float* out_f32, __nv_bfloat16* out_act,
                         float slope, float divisor) {
   Layer& L = v->layers[layer];
   Op op;
@@ -354,7 +355,7 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
   p.bias = L.d_bias;
   p.res_act = res_act;
   p.res_inv_slope = 10.0f;  // 1 / LRELU_SLOPE: every residual tensor was written with slope 0.1
-  p.sum_in = sum_in;
+  p.sum_a = sum_a;
   p.out_f32 = out_f32;
   p.out_act = out_act;
   p.slope = slope;
@@ -365,7 +366,7 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
 
 // One fused launch for  x + c2(lrelu(c1(lrelu(x))))  (pair_tc.cuh).  `in` holds bf16 leaky_relu(x, 0.1).
 static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B, int T, const __nv_bfloat16* in,
-                        const float* sum_in, float* out_f32, __nv_bfloat16* out_act, float slope, float divisor) {
+                        const __nv_bfloat16* sum_a, float* out_f32, __nv_bfloat16* out_act, float slope, float divisor) {
   const Layer& L1 = v->layers[l1];
   const Layer& L2 = v->layers[l2];
   Op op;
@@ -382,7 +383,7 @@ static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B,
   p.bias2 = L2.d_bias;
   p.res_act = in;
   p.res_inv_slope = 10.0f;
-  p.sum_in = sum_in;
+  p.sum_a = sum_a;
   p.out_f32 = out_f32;
   p.out_act = out_act;
   p.slope_mid = 0.1f;
@@ -433,14 +434,15 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
         // where does x_new = conv(...) + x go?
         float* of32 = nullptr;
         __nv_bfloat16* oact = fused ? ((m & 1) ? bf.M : bf.A1) : bf.A1;
-        const float* sum_in = nullptr;
+        const __nv_bfloat16* sum_in = nullptr;
         float divisor = 0.f, slope = kSlope;
         if (last) {
-          oact = nullptr;
-          of32 = bf.SUM;
-          sum_in = j > 0 ? bf.SUM : nullptr;      // xs += resblock_j(x)   (generator.py:44-47)
+          // xs += resblock_j(x) (generator.py:44-47): the running sum is kept in bf16 (slope 1 = no activation),
+          // alternating between S0 and S1 so no launch reads and writes the same buffer
+          oact = (j & 1) ? bf.S1 : bf.S0;
+          slope = 1.0f;
+          sum_in = j > 0 ? ((j & 1) ? bf.S0 : bf.S1) : nullptr;
           if (j + 1 == c.num_kernels) {           // x = xs / num_kernels   (generator.py:48)
-            of32 = nullptr;
             oact = bf.Y;
             divisor = (float)c.num_kernels;
             slope = out_slope;

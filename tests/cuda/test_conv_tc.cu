@@ -64,7 +64,7 @@ static const Cfg kCfgs[] = {
 static const int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 
 __global__ void ref_conv(const __nv_bfloat16* x, const float* wg, const float* bias, const __nv_bfloat16* res,
-                         const float* sum, float* out, int B, int T, int cin, int n_total, int nt, int taps,
+                         const __nv_bfloat16* sum, float* out, int B, int T, int cin, int n_total, int nt, int taps,
                          const int* shifts, int div3) {
   const size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   const size_t total = (size_t)B * T * n_total;
@@ -86,7 +86,7 @@ __global__ void ref_conv(const __nv_bfloat16* x, const float* wg, const float* b
     const float a = __bfloat162float(res[idx]);
     v += a > 0.f ? a : a * 10.0f;
   }
-  if (sum) v += sum[idx];
+  if (sum) v += __bfloat162float(sum[idx]);
   if (div3) v = v / 3.0f;
   out[idx] = v;
 }
@@ -140,8 +140,8 @@ int main(int argc, char** argv) {
                no = (size_t)c.B * c.T * c.n_total;
   std::vector<uint16_t> hx(nx);
   for (auto& v : hx) v = f32_to_bf16_rn(nd(rng));
-  std::vector<float> hw(nw), hb(c.n_total), hsum;
-  std::vector<uint16_t> hres;
+  std::vector<float> hw(nw), hb(c.n_total);
+  std::vector<uint16_t> hres, hsum;
   const float wscale = 1.0f / sqrtf((float)c.cin * c.taps);
   for (auto& v : hw) v = bf16_to_f32(f32_to_bf16_rn(nd(rng) * wscale));
   for (auto& v : hb) v = nd(rng) * 0.1f;
@@ -151,14 +151,14 @@ int main(int argc, char** argv) {
   }
   if (c.sum) {
     hsum.resize(no);
-    for (auto& v : hsum) v = nd(rng);
+    for (auto& v : hsum) v = f32_to_bf16_rn(nd(rng));
   }
   std::vector<uint8_t> hpack(packed_weight_bytes(s));
   pack_conv_weights(s, hw.data(), hpack.data());
 
   __nv_bfloat16 *dx, *dact = nullptr;
-  float *dw, *db, *dsum = nullptr, *dout = nullptr, *dref;
-  __nv_bfloat16* dres = nullptr;
+  float *dw, *db, *dout = nullptr, *dref;
+  __nv_bfloat16 *dres = nullptr, *dsum = nullptr;
   uint8_t* dpack;
   int* dshift;
   CK(cudaMalloc(&dx, nx * 2));
@@ -177,8 +177,8 @@ int main(int argc, char** argv) {
     CK(cudaMemcpy(dres, hres.data(), no * 2, cudaMemcpyHostToDevice));
   }
   if (c.sum) {
-    CK(cudaMalloc(&dsum, no * 4));
-    CK(cudaMemcpy(dsum, hsum.data(), no * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&dsum, no * 2));
+    CK(cudaMemcpy(dsum, hsum.data(), no * 2, cudaMemcpyHostToDevice));
   }
   if (c.f32out) {
     CK(cudaMalloc(&dout, no * 4));
@@ -205,7 +205,7 @@ int main(int argc, char** argv) {
   p.bias = db;
   p.res_act = dres;
   p.res_inv_slope = 10.0f;
-  p.sum_in = dsum;
+  p.sum_a = dsum;
   p.out_f32 = dout;
   p.out_act = dact;
   p.slope = 0.1f;
@@ -281,7 +281,7 @@ int main(int argc, char** argv) {
   printf("  time %.4f ms  -> %.1f TFLOP/s\n", ms, flops / ms * 1e-9);
 #ifdef E2E_TRACE
   {
-    static unsigned long long tr[512][12];
+    static unsigned long long tr[512][16];
     launch_conv(plan, 0);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpyFromSymbol(tr, g_trace, sizeof(tr)));

@@ -73,12 +73,13 @@ __global__ void act_round(const float* in, __nv_bfloat16* out, size_t n, float s
     out[i] = __float2bfloat16(v > 0.f ? v : v * slope);
   }
 }
-__global__ void finish(const float* c2, const __nv_bfloat16* x, const float* sum, float* out, size_t n, int div3) {
+__global__ void finish(const float* c2, const __nv_bfloat16* x, const __nv_bfloat16* sum, float* out, size_t n,
+                       int div3) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i < n) {
     const float a = __bfloat162float(x[i]);
     float v = c2[i] + (a > 0.f ? a : a * 10.0f);
-    if (sum) v += sum[i];
+    if (sum) v += __bfloat162float(sum[i]);
     if (div3) v = v / 3.0f;
     out[i] = v;
   }
@@ -113,7 +114,8 @@ int main(int argc, char** argv) {
   const size_t ne = (size_t)c.B * c.T * c.C, nw = (size_t)c.C * c.k * c.C;
   std::vector<uint16_t> hx(ne);
   for (auto& v : hx) v = f32_to_bf16_rn(nd(rng));
-  std::vector<float> hw1(nw), hw2(nw), hb1(c.C), hb2(c.C), hsum;
+  std::vector<float> hw1(nw), hw2(nw), hb1(c.C), hb2(c.C);
+  std::vector<uint16_t> hsum;
   const float ws = 1.0f / sqrtf((float)c.C * c.k);
   for (auto& v : hw1) v = bf16_to_f32(f32_to_bf16_rn(nd(rng) * ws));
   for (auto& v : hw2) v = bf16_to_f32(f32_to_bf16_rn(nd(rng) * ws));
@@ -121,14 +123,14 @@ int main(int argc, char** argv) {
   for (auto& v : hb2) v = nd(rng) * 0.1f;
   if (c.sum) {
     hsum.resize(ne);
-    for (auto& v : hsum) v = nd(rng);
+    for (auto& v : hsum) v = f32_to_bf16_rn(nd(rng));
   }
   std::vector<uint8_t> hp1(packed_weight_bytes(s)), hp2(packed_weight_bytes(s));
   pack_conv_weights(s, hw1.data(), hp1.data());
   pack_conv_weights(s, hw2.data(), hp2.data());
 
-  __nv_bfloat16 *dx, *dmid, *dact = nullptr;
-  float *dw1, *dw2, *db1, *db2, *dsum = nullptr, *dout = nullptr, *dt1, *dt2, *dref;
+  __nv_bfloat16 *dx, *dmid, *dact = nullptr, *dsum = nullptr;
+  float *dw1, *dw2, *db1, *db2, *dout = nullptr, *dt1, *dt2, *dref;
   uint8_t *dp1, *dp2;
   CK(cudaMalloc(&dx, ne * 2));
   CK(cudaMalloc(&dmid, ne * 2));
@@ -149,8 +151,8 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dp1, hp1.data(), hp1.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dp2, hp2.data(), hp2.size(), cudaMemcpyHostToDevice));
   if (c.sum) {
-    CK(cudaMalloc(&dsum, ne * 4));
-    CK(cudaMemcpy(dsum, hsum.data(), ne * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&dsum, ne * 2));
+    CK(cudaMemcpy(dsum, hsum.data(), ne * 2, cudaMemcpyHostToDevice));
   }
   if (c.f32out) {
     CK(cudaMalloc(&dout, ne * 4));
@@ -179,7 +181,7 @@ int main(int argc, char** argv) {
   p.bias2 = db2;
   p.res_act = dx;
   p.res_inv_slope = 10.0f;
-  p.sum_in = dsum;
+  p.sum_a = dsum;
   p.out_f32 = dout;
   p.out_act = dact;
   p.slope_mid = 0.1f;
@@ -250,16 +252,17 @@ int main(int argc, char** argv) {
   printf("  time %.4f ms  -> %.1f TFLOP/s (algorithmic)\n", ms, flops / ms * 1e-9);
 #ifdef E2E_TRACE
   {
-    static unsigned long long tr[512][12];
-    launch_pair(plan, 0);
+    static unsigned long long tr[512][16];
+    for (int i = 0; i < reps; ++i) launch_pair(plan, 0);  // the traced launch runs in the same power state as the timing loop
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpyFromSymbol(tr, g_trace, sizeof(tr)));
     printf("  trace: cta | kernel us | MMA-thread waits (us): acc_empty m_full w_full a_full | units | epi warp4: epi1 wait/work, epi2 wait/work\n");
     for (int i = 0; i < (int)plan.grid.x && i < 512; i += 49) {
       const int nu = (p.n_units - i + plan.grid.x - 1) / plan.grid.x;
-      printf("  %5d | %8.2f | %8.2f %8.2f %8.2f %8.2f | %d | %7.2f %7.2f %7.2f %7.2f\n", i, (tr[i][7] - tr[i][0]) * 1e-3,
-             tr[i][8] * 1e-3, tr[i][9] * 1e-3, tr[i][10] * 1e-3, tr[i][11] * 1e-3, nu, tr[i][2] * 1e-3, tr[i][3] * 1e-3,
-             tr[i][5] * 1e-3, tr[i][6] * 1e-3);
+      printf("  %5d | %8.2f | %8.2f %8.2f %8.2f %8.2f | %d | %7.2f %7.2f %7.2f %7.2f | sm %.0f MHz\n", i,
+             (tr[i][7] - tr[i][0]) * 1e-3, tr[i][8] * 1e-3, tr[i][9] * 1e-3, tr[i][10] * 1e-3, tr[i][11] * 1e-3, nu,
+             tr[i][2] * 1e-3, tr[i][3] * 1e-3, tr[i][5] * 1e-3, tr[i][6] * 1e-3,
+             (double)(tr[i][13] - tr[i][12]) / (double)(tr[i][7] - tr[i][0]) * 1e3);
     }
   }
 #endif
