@@ -1,5 +1,6 @@
 // Host side of the fused residual-pair kernel (pair_tc.cuh): geometry planning and launch.
 #pragma once
+#include <cstdlib>
 #include "conv_host.cuh"
 #include "pair_tc.cuh"
 
@@ -7,11 +8,42 @@ namespace e2e {
 
 struct PairPlan {
   PairParams p{};
-  CUtensorMap tm{};
+  CUtensorMap tm{};            // input activation [B][T][C]
+  CUtensorMap tm_w1{}, tm_w2{};  // packed weight images as [rows][rowb] matrices (CTA-pair form only)
   dim3 grid{};
   int smem_bytes = 0;
   int rowb = 128, mt = 1;
+  int cg = 1;                  // CTAs per MMA (tcgen05 cta_group): 2 = CTA pairs in 2-CTA clusters
 };
+
+// CTA pairs pay off where the MMAs dominate and the one-CTA form is bound by shared-memory traffic (B operand
+// reads + the weight stream).  Measured in the full forward on B200 (16 x 5 s, per launch, one-CTA -> pair):
+//   C = 128: k = 11  307 -> 257 us, k = 7  201 -> 190 us, k = 3  122 -> 151 us (epilogue-latency bound: loses to the
+//   C =  64: k = 11  182 -> 169 us, k = 7  124 -> 151 us                         extra cross-CTA hops)
+//   C =  32: k = 11  147 -> 139 us, k = 7  106 -> 134 us
+// E2E_PAIR_CG=1|2 overrides for experiments.
+inline int pair_cta_group(int C, int k) {
+  const char* e = std::getenv("E2E_PAIR_CG");
+  if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+  if (C >= 128) return k >= 7 ? 2 : 1;
+  return k >= 11 ? 2 : 1;
+}
+
+// 2-D tensor map over a packed weight image: rows of `rowb` bytes, box = half a tile (nt/2 rows), no swizzle (the
+// image already holds the swizzled bytes).
+inline int make_weight_tensor_map(CUtensorMap* tm, const void* base, int rows, int rowb, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(-10, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)(rowb / 2), (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)rowb};
+  cuuint32_t box[2] = {(cuuint32_t)(rowb / 2), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-11, "cuTensorMapEncodeTiled failed for a weight image");
+  return 0;
+}
 
 // The fused pair needs 4 TMEM accumulators of 128*MT x C fp32 (two units in flight x two convs) and two input
 // slabs + two intermediate slabs in shared memory: supported for C in {32, 64, 128} with MT = 128 / C.
@@ -26,7 +58,8 @@ inline int plan_pair(PairPlan& plan, int C, int k, int d, int B, int T, int n_sm
   PairParams& p = plan.p;
   plan.rowb = C == 32 ? 64 : 128;
   plan.mt = 128 / C;
-  const int rowb = plan.rowb, mt = plan.mt;
+  plan.cg = pair_cta_group(C, k);
+  const int rowb = plan.rowb, mt = plan.mt, cg = plan.cg;
   p.T = T;
   p.B = B;
   p.panels = C == 32 ? 1 : C / 64;
@@ -36,7 +69,7 @@ inline int plan_pair(PairPlan& plan, int C, int k, int d, int B, int T, int n_sm
   p.r_out = 128 * mt - (k - 1);
   p.m_rows = (128 * mt + (k - 1) + 15) / 16 * 16;
   const int need = 128 * mt + (k - 1) * d;
-  const int tile_bytes = C * rowb;
+  const int tile_bytes = C * rowb / cg;  // per CTA: a pair splits every weight tile
   const int total_tiles = p.panels * k;
   const int budget = kSmemLimit - 1024 - kPairTailBytes;
   for (int box = 128; box >= 16; box >>= 1) {
@@ -58,18 +91,33 @@ inline int plan_pair(PairPlan& plan, int C, int k, int d, int B, int T, int n_sm
       p.tiles_per_b = (T + p.r_out - 1) / p.r_out;
       p.n_units = B * p.tiles_per_b;
       plan.smem_bytes = 1024 + slabs + stages * stage_bytes + kPairTailBytes;
-      plan.grid = dim3(p.n_units < n_sms ? p.n_units : n_sms, 1, 1);
+      int grid = (p.n_units + cg - 1) / cg * cg;
+      if (grid > n_sms) grid = n_sms / cg * cg;
+      plan.grid = dim3(grid, 1, 1);
       return 0;
     }
   }
   return fail(-3, "fused pair does not fit shared memory");
 }
 
-typedef void (*PairKernelFn)(const CUtensorMap, const PairParams);
+// Fills plan.tm_w1 / tm_w2 (needed by the CTA-pair form; harmless otherwise).  w1 / w2 = packed images of c1 / c2.
+inline int pair_weight_maps(PairPlan& plan, const void* w1, const void* w2) {
+  const PairParams& p = plan.p;
+  const int rows = p.panels * p.taps * p.nt;
+  int rc = make_weight_tensor_map(&plan.tm_w1, w1, rows, plan.rowb, p.nt / 2);
+  if (rc) return rc;
+  return make_weight_tensor_map(&plan.tm_w2, w2, rows, plan.rowb, p.nt / 2);
+}
 
-inline PairKernelFn pair_kernel_for(int rowb, int mt) {
-  if (rowb == 64) return pair_tc_kernel<64, 4>;
-  return mt == 2 ? pair_tc_kernel<128, 2> : pair_tc_kernel<128, 1>;
+typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const PairParams);
+
+inline PairKernelFn pair_kernel_for(int rowb, int mt, int cg) {
+  if (cg == 2) {
+    if (rowb == 64) return pair_tc_kernel<64, 4, 2>;
+    return mt == 2 ? pair_tc_kernel<128, 2, 2> : pair_tc_kernel<128, 1, 2>;
+  }
+  if (rowb == 64) return pair_tc_kernel<64, 4, 1>;
+  return mt == 2 ? pair_tc_kernel<128, 2, 1> : pair_tc_kernel<128, 1, 1>;
 }
 
 inline int pair_kernels_init() {
@@ -77,7 +125,8 @@ inline int pair_kernels_init() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (done_for_device == dev) return 0;
-  PairKernelFn fns[3] = {pair_tc_kernel<64, 4>, pair_tc_kernel<128, 2>, pair_tc_kernel<128, 1>};
+  PairKernelFn fns[6] = {pair_tc_kernel<64, 4, 1>, pair_tc_kernel<128, 2, 1>, pair_tc_kernel<128, 1, 1>,
+                         pair_tc_kernel<64, 4, 2>, pair_tc_kernel<128, 2, 2>, pair_tc_kernel<128, 1, 2>};
   for (PairKernelFn f : fns) {
     cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return fail((int)e, std::string("cudaFuncSetAttribute(pair): ") + cudaGetErrorString(e));
@@ -89,8 +138,22 @@ inline int pair_kernels_init() {
 inline int launch_pair(const PairPlan& plan, cudaStream_t st) {
   int rc = pair_kernels_init();
   if (rc) return rc;
-  pair_kernel_for(plan.rowb, plan.mt)<<<plan.grid, kConvThreads, plan.smem_bytes, st>>>(plan.tm, plan.p);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = plan.grid;
+  cfg.blockDim = dim3(kConvThreads, 1, 1);
+  cfg.dynamicSmemBytes = plan.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan.cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, pair_kernel_for(plan.rowb, plan.mt, plan.cg), plan.tm, plan.tm_w1, plan.tm_w2,
+                                     plan.p);
+  if (e != cudaSuccess) return fail((int)e, std::string("pair_tc launch: ") + cudaGetErrorString(e));
+  e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("pair_tc launch: ") + cudaGetErrorString(e));
   return 0;
 }

@@ -18,6 +18,15 @@
 // so the epilogue of every job overlaps the MMAs of the next one.  Roles: warp 0 slab producer (TMA), warp 1
 // weight producer (bulk copies, both convs, job order), warp 2 MMA issuer, warp 3 TMEM allocator, warps 4-19
 // epilogue (four per TMEM lane quarter, 16-column items, epilogue.cuh).
+//
+// CG = 2 runs the same pipeline on a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2): each CTA owns its units, its
+// slabs and its epilogue, but one thread of the even CTA issues M = 256 MMAs whose rows 0-127 / 128-255 are the two
+// CTAs' units and whose B operand (the weight tile) is split between them, N/2 rows each.  Per CTA that halves the
+// weight bytes streamed from L2 into shared memory and the B-operand bytes every MMA reads back out of it - the
+// two things that cap the N = 128 MMAs of the C = 128 stage below the tensor-pipe rate in the one-CTA form.
+// All "full" barriers the issuing thread waits on live in the even CTA (TMA .cta_group::2 loads of both CTAs
+// count their bytes there, the odd CTA's epilogue warps arrive there remotely); every tcgen05.commit is
+// multicast to both CTAs.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -49,9 +58,10 @@ struct PairParams {
   __nv_bfloat16* out_act;
 };
 
-template <int ROWB, int MT>
+template <int ROWB, int MT, int CG>
 __global__ void __launch_bounds__(kConvThreads, 1)
-pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
+pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w1,
+               const __grid_constant__ CUtensorMap tm_w2, const PairParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -67,8 +77,10 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
   const int m_panel_bytes = p.m_rows * ROWB;
   const int a_lane_bytes = p.panels * a_panel_bytes;
   const int m_lane_bytes = p.panels * m_panel_bytes;
-  const int tile_bytes = p.nt * ROWB;
+  const int tile_bytes = p.nt * ROWB / CG;  // bytes of one weight tile (one tap of one panel) held by THIS CTA
   const int total_tiles = p.panels * p.taps;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool cta_leader = rank == 0;
   const int h1 = (p.taps - 1) / 2 * p.dil, h2 = (p.taps - 1) / 2;
   const int acc_cols = MT * p.nt;  // TMEM columns per accumulator; 4 accumulators: [lane][conv]
 
@@ -87,8 +99,12 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
   float* s_bias1 = reinterpret_cast<float*>(bars + 64);  // [nt] biases of c1 / c2, staged once (512 B past `bars`)
   float* s_bias2 = s_bias1 + 128;
 
-  // units of this CTA: u_n = blockIdx.x + n * gridDim.x, n = 0 .. N-1
-  const int N = (p.n_units - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // units of this CTA: u_n = CG * (cluster + n * n_clusters) + rank, n = 0 .. N-1.  N is the same for both CTAs of
+  // a pair; a unit index >= n_units is a dummy (utterance index B: TMA zero-fills, nothing is stored).
+  const int cluster_id = (int)blockIdx.x / CG, n_clusters = (int)gridDim.x / CG;
+  const int n_super = (p.n_units + CG - 1) / CG;
+  const int N = (n_super - cluster_id + n_clusters - 1) / n_clusters;
+  const int u_first = CG * cluster_id + (int)rank, u_step = CG * n_clusters;
 
   if (threadIdx.x == 0) {
     E2E_TR(0);
@@ -108,22 +124,28 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], kEpiWarps);
+      mbar_init(&acc_empty[i], kEpiWarps * CG);  // (the even CTA's copy collects both CTAs' epilogue warps)
     }
-    mbar_init(&m_full[0], kEpiWarps);
-    mbar_init(&m_full[1], kEpiWarps);
+    mbar_init(&m_full[0], kEpiWarps * CG);
+    mbar_init(&m_full[1], kEpiWarps * CG);
     fence_mbar_init();
   }
   if (warp == 3) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair(tmem_slot, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   for (int i = threadIdx.x; i < p.nt; i += blockDim.x) {
     s_bias1[i] = p.bias1[i];
     s_bias2[i] = p.bias2[i];
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's mbarriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) E2E_TR(1);
@@ -133,19 +155,24 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
       // ---------------- input slab producer (TMA) ----------------
       const int boxes = p.a_rows / p.box_rows;
       UnitIter uit;
-      uit.init(blockIdx.x, gridDim.x, 1, p.tiles_per_b);
+      uit.init(u_first, u_step, 1, p.tiles_per_b);
       for (int n = 0; n < N; ++n, uit.next()) {
-        const int b = uit.b;
+        const int b = uit.b;  // == B for a dummy unit: every row is out of bounds and arrives as zeros
         const int t0 = uit.tile * p.r_out;
         const int ln = n & 1;
         const uint32_t par = ((n >> 1) & 1) ^ 1;
         for (int pn = 0; pn < p.panels; ++pn) {
           mbar_wait(&a_empty[ln * 4 + pn], par, 0x100 + ln * 4 + pn);
-          mbar_arrive_expect_tx(&a_full[ln * 4 + pn], a_panel_bytes);
+          if (cta_leader) mbar_arrive_expect_tx(&a_full[ln * 4 + pn], a_panel_bytes * CG);
           uint8_t* dst = a_slab + ln * a_lane_bytes + pn * a_panel_bytes;
-          for (int bx = 0; bx < boxes; ++bx)
-            tma_load_3d(dst + bx * p.box_rows * ROWB, &tm_in, pn * CH_PANEL, t0 - h2 - h1 + bx * p.box_rows, b,
-                        &a_full[ln * 4 + pn]);
+          for (int bx = 0; bx < boxes; ++bx) {
+            if (CG == 2)
+              tma_load_3d_pair(dst + bx * p.box_rows * ROWB, &tm_in, pn * CH_PANEL, t0 - h2 - h1 + bx * p.box_rows, b,
+                               &a_full[ln * 4 + pn]);
+            else
+              tma_load_3d(dst + bx * p.box_rows * ROWB, &tm_in, pn * CH_PANEL, t0 - h2 - h1 + bx * p.box_rows, b,
+                          &a_full[ln * 4 + pn]);
+          }
         }
       }
     }
@@ -153,15 +180,23 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
     if (lane == 0) {
       // ---------------- weight producer: job order c1(u0) | c1(u1) c2(u0) | ... ----------------
       uint32_t stage = 0, par = 1;
-      auto stream = [&](const uint8_t* wsrc) {
+      auto stream = [&](const uint8_t* wsrc, const CUtensorMap* tmw) {
         int first = 0;
         for (int c = 0; c < p.n_chunks; ++c, first += p.tiles_per_chunk) {
           mbar_wait(&w_empty[stage], par, 0x200 + stage);
           const int ntile = min(p.tiles_per_chunk, total_tiles - first);
           const uint32_t bytes = ntile * tile_bytes;
-          mbar_arrive_expect_tx(&w_full[stage], bytes);
-          bulk_load_1d(ring + stage * p.stage_bytes, wsrc + static_cast<size_t>(first) * tile_bytes, bytes,
-                       &w_full[stage]);
+          if (CG == 2) {
+            // this CTA's half (N/2 rows) of every tile of the chunk; the packed image is a [rows][ROWB] matrix
+            if (cta_leader) mbar_arrive_expect_tx(&w_full[stage], bytes * 2);
+            for (int i = 0; i < ntile; ++i)
+              tma_load_2d_pair(ring + stage * p.stage_bytes + i * tile_bytes, tmw, 0,
+                               (first + i) * p.nt + (int)rank * (p.nt / 2), &w_full[stage]);
+          } else {
+            mbar_arrive_expect_tx(&w_full[stage], bytes);
+            bulk_load_1d(ring + stage * p.stage_bytes, wsrc + static_cast<size_t>(first) * tile_bytes, bytes,
+                         &w_full[stage]);
+          }
           if (++stage == (uint32_t)p.n_stages) {
             stage = 0;
             par ^= 1;
@@ -169,14 +204,22 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
         }
       };
       for (int n = 0; n <= N; ++n) {
-        if (n < N) stream(p.w1);
-        if (n >= 1) stream(p.w2);
+        if (n < N) stream(p.w1, &tm_w1);
+        if (n >= 1) stream(p.w2, &tm_w2);
       }
     }
-  } else if (warp == 2) {
-    // ---------------- MMA issuer (warp-uniform loop, one elected lane issues) ----------------
+  } else if (warp == 2 && cta_leader) {
+    // ---------------- MMA issuer (warp-uniform loop, one elected lane issues; even CTA only) ----------------
     const bool leader = elect_one();
-    const uint32_t idesc = umma_idesc_bf16(128, p.nt);
+    const uint32_t idesc = umma_idesc_bf16(128 * CG, p.nt);
+    auto wait_full = [&](uint64_t* bar, uint32_t par, uint32_t code) {
+      if (CG == 2) mbar_wait_cluster(bar, par, code);
+      else mbar_wait(bar, par, code);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (CG == 2) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
     const uint32_t a_lo0 = ((smem_u32(a_slab) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t m_lo0 = ((smem_u32(m_slab) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -192,11 +235,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
 #ifdef E2E_TRACE
       unsigned long long tq = gtime_ns();
 #endif
-      mbar_wait(&acc_empty[ln * 2 + ci], par ^ 1, 0x300 + ln * 2 + ci);
+      wait_full(&acc_empty[ln * 2 + ci], par ^ 1, 0x300 + ln * 2 + ci);
 #ifdef E2E_TRACE
       if (leader && blockIdx.x < 512) { const unsigned long long t2 = gtime_ns(); g_trace[blockIdx.x][8] += t2 - tq; tq = t2; }
 #endif
-      if (ci == 1) mbar_wait(&m_full[ln], par, 0x380 + ln);  // c1's epilogue has written the whole M slab
+      if (ci == 1) wait_full(&m_full[ln], par, 0x380 + ln);  // c1's epilogue has written the whole M slab
 #ifdef E2E_TRACE
       if (leader && blockIdx.x < 512) g_trace[blockIdx.x][9] += gtime_ns() - tq;
 #endif
@@ -208,7 +251,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
 #ifdef E2E_TRACE
         const unsigned long long tw = gtime_ns();
 #endif
-        mbar_wait(&w_full[stage], wpar, 0x400 + stage);
+        wait_full(&w_full[stage], wpar, 0x400 + stage);
         tc_fence_after_sync();
 #ifdef E2E_TRACE
         if (leader && blockIdx.x < 512) g_trace[blockIdx.x][10] += gtime_ns() - tw;
@@ -221,7 +264,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
 #ifdef E2E_TRACE
             const unsigned long long ta = gtime_ns();
 #endif
-            mbar_wait(&a_full[ln * 4 + pn], par, 0x500 + ln * 4 + pn);
+            wait_full(&a_full[ln * 4 + pn], par, 0x500 + ln * 4 + pn);
             tc_fence_after_sync();
 #ifdef E2E_TRACE
             if (leader && blockIdx.x < 512) g_trace[blockIdx.x][11] += gtime_ns() - ta;
@@ -235,27 +278,34 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
               for (int ks = 0; ks < KS; ++ks) {
                 const uint64_t da = (static_cast<uint64_t>(DESC_HI) << 32) | (s_lo + m * (128 * ROW16) + ks * 2);
                 const uint64_t db = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + ks * 2);
-                if (ks == 0)
-                  umma_bf16(d_tmem + m * p.nt, da, db, idesc, accum);
-                else
-                  umma_bf16_acc(d_tmem + m * p.nt, da, db, idesc);
+                if (CG == 2) {
+                  if (ks == 0)
+                    umma_bf16_pair(d_tmem + m * p.nt, da, db, idesc, accum);
+                  else
+                    umma_bf16_acc_pair(d_tmem + m * p.nt, da, db, idesc);
+                } else {
+                  if (ks == 0)
+                    umma_bf16(d_tmem + m * p.nt, da, db, idesc, accum);
+                  else
+                    umma_bf16_acc(d_tmem + m * p.nt, da, db, idesc);
+                }
               }
             }
           }
           accum = 1;
           if (++tap == p.taps) {
-            if (ci == 0 && leader) umma_commit(&a_empty[ln * 4 + pn]);  // input panel consumed -> TMA may refill
+            if (ci == 0 && leader) commit(&a_empty[ln * 4 + pn]);  // input panel consumed -> TMA may refill
             tap = 0;
             ++pn;
           }
         }
-        if (leader) umma_commit(&w_empty[stage]);
+        if (leader) commit(&w_empty[stage]);
         if (++stage == (uint32_t)p.n_stages) {
           stage = 0;
           wpar ^= 1;
         }
       }
-      if (leader) umma_commit(&acc_full[ln * 2 + ci]);
+      if (leader) commit(&acc_full[ln * 2 + ci]);
     };
     for (int n = 0; n <= N; ++n) {
       if (n < N) job(n, 0);
@@ -344,8 +394,13 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
       fence_proxy_async_smem();  // the M slab is read by the tensor core through the async proxy
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(&acc_empty[ln * 2 + 0]);
-        mbar_arrive(&m_full[ln]);
+        if (CG == 2) {  // the issuing thread waits in the even CTA
+          mbar_arrive_remote(&acc_empty[ln * 2 + 0], 0);
+          mbar_arrive_remote(&m_full[ln], 0);
+        } else {
+          mbar_arrive(&acc_empty[ln * 2 + 0]);
+          mbar_arrive(&m_full[ln]);
+        }
       }
 #ifdef E2E_TRACE
       if (threadIdx.x == 128 && blockIdx.x < 512) {
@@ -363,8 +418,8 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
     bool va = false, vb = false;
     auto prefetch_res = [&](int b, int t0) {
       const int oa = mA * 128 + row_in_tile, ob = mB * 128 + row_in_tile;
-      va = oa < p.r_out && t0 + oa < p.T;
-      vb = ob < p.r_out && t0 + ob < p.T;
+      va = oa < p.r_out && t0 + oa < p.T && b < p.B;
+      vb = ob < p.r_out && t0 + ob < p.T && b < p.B;
       offa = (static_cast<size_t>(b) * p.T + (va ? t0 + oa : 0)) * p.nt + ccA * 16;
       offb = (static_cast<size_t>(b) * p.T + (vb ? t0 + ob : 0)) * p.nt + ccB * 16;
       rqa[0] = rqa[1] = rqb[0] = rqb[1] = make_uint4(0u, 0u, 0u, 0u);
@@ -403,7 +458,10 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
       // every TMEM read of this warp has completed: release the accumulator before the global stores of item B
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[ln * 2 + 1]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_remote(&acc_empty[ln * 2 + 1], 0);
+        else mbar_arrive(&acc_empty[ln * 2 + 1]);
+      }
       epi_finish16(vB, bv, rqb, sqb, eo, offb, vb);
 #ifdef E2E_TRACE
       if (threadIdx.x == 128 && blockIdx.x < 512) {
@@ -414,7 +472,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
     };
 
     UnitIter uit;
-    uit.init(blockIdx.x, gridDim.x, 1, p.tiles_per_b);
+    uit.init(u_first, u_step, 1, p.tiles_per_b);
     int pb = 0, pt0 = 0;  // unit n - 1
     for (int n = 0; n <= N; ++n) {
       if (n >= 1) prefetch_res(pb, pt0);
@@ -428,10 +486,13 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const PairParams p) {
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  __syncwarp();
+  if (CG == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair's MMAs can still touch it
+  else __syncthreads();
   if (warp == 3) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 512);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
   if (threadIdx.x == 0) E2E_TR(7);
 }

@@ -379,6 +379,8 @@ static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B,
   if (rc) return rc;
   p.w1 = L1.d_w;
   p.w2 = L2.d_w;
+  rc = pair_weight_maps(op.pair, L1.d_w, L2.d_w);
+  if (rc) return rc;
   p.bias1 = L1.d_bias;
   p.bias2 = L2.d_bias;
   p.res_act = in;

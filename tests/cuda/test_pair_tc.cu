@@ -177,6 +177,11 @@ int main(int argc, char** argv) {
   }
   p.w1 = dp1;
   p.w2 = dp2;
+  rc = pair_weight_maps(plan, dp1, dp2);
+  if (rc) {
+    printf("weight tensor maps failed: %s\n", last_error().c_str());
+    return 3;
+  }
   p.bias1 = db1;
   p.bias2 = db2;
   p.res_act = dx;
@@ -187,8 +192,8 @@ int main(int argc, char** argv) {
   p.slope_mid = 0.1f;
   p.slope = 0.1f;
   p.divisor = c.div3 ? 3.0f : 0.f;
-  printf("  plan: grid=%d units=%d smem=%d mt=%d a_rows=%d box=%d m_rows=%d r_out=%d stages=%d stage_bytes=%d chunks=%d\n",
-         plan.grid.x, p.n_units, plan.smem_bytes, plan.mt, p.a_rows, p.box_rows, p.m_rows, p.r_out, p.n_stages,
+  printf("  plan: cg=%d grid=%d units=%d smem=%d mt=%d a_rows=%d box=%d m_rows=%d r_out=%d stages=%d stage_bytes=%d chunks=%d\n",
+         plan.cg, plan.grid.x, p.n_units, plan.smem_bytes, plan.mt, p.a_rows, p.box_rows, p.m_rows, p.r_out, p.n_stages,
          p.stage_bytes, p.n_chunks);
   rc = launch_pair(plan, 0);
   if (rc) {
