@@ -61,7 +61,8 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = build_native()
+    # E2E_TTS_B200_LIB: load another in-tree build of the same sources (A/B experiments on the GPU box)
+    path = os.environ.get("E2E_TTS_B200_LIB") or build_native()
     if not os.path.exists(path):
         raise ImportError("e2e_tts_b200: CUDA library %s is missing and could not be built" % LIB_PATH)
     handle = ctypes.CDLL(path)

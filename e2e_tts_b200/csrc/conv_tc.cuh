@@ -89,6 +89,31 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 #define E2E_TR(slot)
 #endif
 
+#ifdef E2E_TRACE2
+// Debug build only: SM-clock cycles spent in each segment of the epilogue loop by one epilogue thread (warp 4,
+// lane 0) of every CTA, accumulated in registers and written once at the end (E2E_TR2_FLUSH).
+__device__ unsigned int g_trace2[512][24];
+#define E2E_TR2_DECL                                                      \
+  const bool tr2_on = threadIdx.x == 128 && blockIdx.x < 512;             \
+  unsigned int tr2_acc[16];                                               \
+  _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) tr2_acc[i_] = 0;      \
+  unsigned int tr2_last = (unsigned int)clock64();
+#define E2E_TR2(k)                                                        \
+  do {                                                                    \
+    const unsigned int c_ = (unsigned int)clock64();                      \
+    tr2_acc[k] += c_ - tr2_last;                                          \
+    tr2_last = c_;                                                        \
+  } while (0)
+#define E2E_TR2_FLUSH                                                     \
+  if (tr2_on) {                                                           \
+    _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) g_trace2[blockIdx.x][i_] = tr2_acc[i_]; \
+  }
+#else
+#define E2E_TR2_DECL
+#define E2E_TR2(k)
+#define E2E_TR2_FLUSH
+#endif
+
 template <int ROWB, int MT>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {

@@ -332,6 +332,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     eo.scale = p.divisor != 0.f ? 1.0f / p.divisor : 0.f;
     eo.inv = p.res_inv_slope;
     const float smid = p.slope_mid;
+    E2E_TR2_DECL
 
     // one 16-column item of c1: acc + bias1 -> leaky_relu -> bf16 -> M slab (zero outside the utterance)
     auto store_mid = [&](const uint32_t (&v)[16], const float4 (&bv)[4], int m, int cc, int t0, uint8_t* mdst) {
@@ -376,6 +377,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #endif
       mbar_wait(&acc_full[ln * 2 + 0], par, 0x600 + ln * 2);
       tc_fence_after_sync();
+      E2E_TR2(2);
 #ifdef E2E_TRACE
       const unsigned long long te1 = gtime_ns();
 #endif
@@ -385,11 +387,15 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       tmem_ld_32x16(d_tmem + mA * p.nt + ccA * 16, vA);
       lds_bias(s_bias1, ccA, bv);
       tmem_ld_wait();
+      E2E_TR2(3);
       tmem_ld_32x16(d_tmem + mB * p.nt + ccB * 16, vB);
       store_mid(vA, bv, mA, ccA, t0, mdst);
+      E2E_TR2(4);
       lds_bias(s_bias1, ccB, bv);
       tmem_ld_wait();
+      E2E_TR2(5);
       store_mid(vB, bv, mB, ccB, t0, mdst);
+      E2E_TR2(6);
       tc_fence_before_sync();
       fence_proxy_async_smem();  // the M slab is read by the tensor core through the async proxy
       __syncwarp();
@@ -402,6 +408,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
           mbar_arrive(&m_full[ln]);
         }
       }
+      E2E_TR2(7);
 #ifdef E2E_TRACE
       if (threadIdx.x == 128 && blockIdx.x < 512) {
         g_trace[blockIdx.x][2] += te1 - te0;           // epi1: waiting for the accumulator
@@ -442,6 +449,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #endif
       mbar_wait(&acc_full[ln * 2 + 1], par, 0x700 + ln * 2);
       tc_fence_after_sync();
+      E2E_TR2(8);
 #ifdef E2E_TRACE
       const unsigned long long tf1 = gtime_ns();
 #endif
@@ -451,10 +459,13 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       tmem_ld_32x16(d_tmem + mA * p.nt + ccA * 16, vA);
       lds_bias(s_bias2, ccA, bv);
       tmem_ld_wait();
+      E2E_TR2(9);
       tmem_ld_32x16(d_tmem + mB * p.nt + ccB * 16, vB);
       epi_finish16(vA, bv, rqa, sqa, eo, offa, va);
+      E2E_TR2(10);
       lds_bias(s_bias2, ccB, bv);
       tmem_ld_wait();
+      E2E_TR2(11);
       // every TMEM read of this warp has completed: release the accumulator before the global stores of item B
       tc_fence_before_sync();
       __syncwarp();
@@ -463,6 +474,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         else mbar_arrive(&acc_empty[ln * 2 + 1]);
       }
       epi_finish16(vB, bv, rqb, sqb, eo, offb, vb);
+      E2E_TR2(12);
 #ifdef E2E_TRACE
       if (threadIdx.x == 128 && blockIdx.x < 512) {
         g_trace[blockIdx.x][5] += tf1 - tf0;           // epi2: waiting for the accumulator
@@ -475,7 +487,9 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     uit.init(u_first, u_step, 1, p.tiles_per_b);
     int pb = 0, pt0 = 0;  // unit n - 1
     for (int n = 0; n <= N; ++n) {
+      E2E_TR2(0);
       if (n >= 1) prefetch_res(pb, pt0);
+      E2E_TR2(1);
       const int t0 = uit.tile * p.r_out;
       if (n < N) epi1(n, t0);
       if (n >= 1) epi2(n - 1);
@@ -483,6 +497,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       pt0 = t0;
       uit.next();
     }
+    E2E_TR2_FLUSH
   }
 
   tc_fence_before_sync();

@@ -271,6 +271,26 @@ int main(int argc, char** argv) {
     }
   }
 #endif
+#ifdef E2E_TRACE2
+  {
+    static unsigned int tr2[512][24];
+    launch_pair(plan, 0);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpyFromSymbol(tr2, g_trace2, sizeof(tr2)));
+    const char* nm[13] = {"loop", "prefetch", "e1 wait", "e1 ldA", "e1 midA", "e1 ldB", "e1 midB", "e1 fence+arrive",
+                          "e2 wait", "e2 ldA", "e2 finA", "e2 ldB+rel", "e2 finB"};
+    for (int i = 0; i < (int)plan.grid.x && i < 512; i += 73) {
+      const int nu = (p.n_units - i + plan.grid.x - 1) / plan.grid.x;
+      printf("  trace2 cta %d (%d units), cycles per unit:", i, nu);
+      double tot = 0;
+      for (int k = 0; k < 13; ++k) {
+        printf(" %s=%.0f", nm[k], (double)tr2[i][k] / nu);
+        tot += (double)tr2[i][k] / nu;
+      }
+      printf(" | total=%.0f\n", tot);
+    }
+  }
+#endif
   const bool ok = bad == 0 && bad2 == 0;
   printf("[pair %d] %s\n", id, ok ? "PASS" : "FAIL");
   return ok ? 0 : 1;
