@@ -3,6 +3,7 @@
 // shared-memory images the kernel streams with 1-D bulk copies.
 #pragma once
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,6 +50,22 @@ inline int make_act_tensor_map(CUtensorMap* tm, const void* base, int B, int T, 
   return 0;
 }
 
+// 2-D tensor map over a packed weight image: rows of `rowb` bytes, box = half a tile (nt/2 rows), no swizzle (the
+// image already holds the swizzled bytes).
+inline int make_weight_tensor_map(CUtensorMap* tm, const void* base, int rows, int rowb, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(-10, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)(rowb / 2), (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)rowb};
+  cuuint32_t box[2] = {(cuuint32_t)(rowb / 2), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-11, "cuTensorMapEncodeTiled failed for a weight image");
+  return 0;
+}
+
 // Static description of one convolution layer as the GEMM the kernel runs.
 struct ConvShape {
   int cin;       // padded input channels (32, or a multiple of 64)
@@ -63,15 +80,29 @@ constexpr int kSmemLimit = 232448;  // 227 KB opt-in maximum per CTA on sm_100
 struct ConvPlan {
   ConvParams p{};
   CUtensorMap tm{};
+  CUtensorMap tm_w{};  // packed weight image as a [rows][rowb] matrix (CTA-pair form only)
   dim3 grid{};
   int smem_bytes = 0;
+  int cg = 1;          // CTAs per MMA (tcgen05 cta_group): 2 = CTA pairs in 2-CTA clusters
 };
+
+// CTA pairs for the unfused convolutions: only layers with a single N tile (both CTAs of a pair must use the same
+// weight tiles), and where the weight stream + B operand reads dominate shared-memory traffic: wide N.
+// E2E_CONV_CG=1|2 overrides for experiments.
+inline int conv_cta_group(const ConvShape& s) {
+  if (s.n_total != s.nt || s.nt < 128 || (s.nt / 2) % 8) return 1;
+  const char* e = std::getenv("E2E_CONV_CG");
+  if (e && (e[0] == '1' || e[0] == '2')) return e[0] - '0';
+  return s.nt >= 256 && s.taps >= 7 ? 2 : 1;
+}
 
 // Fill every geometry field of plan.p from the layer shape and the problem size.  `mt_pref` = preferred
 // number of 128-row tiles per unit (1, 2 or 4; reduced until TMEM and shared memory fit); `n_sms` sizes the
 // persistent grid.
-inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pref, int n_sms = 148) {
+inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pref, int n_sms = 148, int cg = 0) {
   ConvParams& p = plan.p;
+  if (cg == 0) cg = conv_cta_group(s);
+  plan.cg = cg;
   if (s.cin != 32 && s.cin % 64 != 0) return fail(-2, "cin must be 32 or a multiple of 64");
   if (s.nt % 32 != 0 || s.nt > 256 || s.n_total % s.nt != 0) return fail(-2, "bad N tiling");
   const int n_tiles = s.n_total / s.nt;
@@ -95,7 +126,7 @@ inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pr
       smax = sh > smax ? sh : smax;
     }
   p.hl = -smin;
-  const int tile_bytes = s.nt * p.rowb;
+  const int tile_bytes = s.nt * p.rowb / cg;  // per CTA: a pair splits every weight tile
   const int total_tiles = p.panels * s.taps;
   // ring stage ~ 32 KB (one tile when a tile is that large): fewer barrier round trips for the MMA issuer
   int tpc = 32768 / tile_bytes;
@@ -129,7 +160,9 @@ inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pr
         p.tiles_per_b = (T + 128 * mt - 1) / (128 * mt);
         p.n_units = B * p.tiles_per_b * n_tiles;
         plan.smem_bytes = 1024 + slots * panel_bytes + stages * p.stage_bytes + bar_bytes;
-        plan.grid = dim3(p.n_units < n_sms ? p.n_units : n_sms, 1, 1);
+        int grid = (p.n_units + cg - 1) / cg * cg;
+        if (grid > n_sms) grid = n_sms / cg * cg;
+        plan.grid = dim3(grid, 1, 1);
         return 0;
       }
     }
@@ -137,11 +170,21 @@ inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pr
   return fail(-3, "convolution does not fit shared memory / TMEM");
 }
 
-typedef void (*ConvKernelFn)(const CUtensorMap, const ConvParams);
+typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const ConvParams);
 
-inline ConvKernelFn conv_kernel_for(int rowb, int mt) {
-  if (rowb == 128) return mt == 4 ? conv_tc_kernel<128, 4> : (mt == 2 ? conv_tc_kernel<128, 2> : conv_tc_kernel<128, 1>);
-  return mt == 4 ? conv_tc_kernel<64, 4> : (mt == 2 ? conv_tc_kernel<64, 2> : conv_tc_kernel<64, 1>);
+inline ConvKernelFn conv_kernel_for(int rowb, int mt, int cg = 1) {
+  if (cg == 2)  // CTA pairs: 64-channel panels only (wide layers)
+    return mt == 4 ? conv_tc_kernel<128, 4, 2> : (mt == 2 ? conv_tc_kernel<128, 2, 2> : conv_tc_kernel<128, 1, 2>);
+  if (rowb == 128)
+    return mt == 4 ? conv_tc_kernel<128, 4, 1> : (mt == 2 ? conv_tc_kernel<128, 2, 1> : conv_tc_kernel<128, 1, 1>);
+  return mt == 4 ? conv_tc_kernel<64, 4, 1> : (mt == 2 ? conv_tc_kernel<64, 2, 1> : conv_tc_kernel<64, 1, 1>);
+}
+
+// Fills plan.tm_w (needed by the CTA-pair form; harmless otherwise).  w = packed image of the layer.
+inline int conv_weight_map(ConvPlan& plan, const void* w) {
+  const ConvParams& p = plan.p;
+  const int rows = p.n_tiles * p.panels * p.taps * p.nt;
+  return make_weight_tensor_map(&plan.tm_w, w, rows, p.rowb, p.nt / 2);
 }
 
 // Opt every instantiation into the 227 KB dynamic shared-memory limit (once per process and device).
@@ -151,11 +194,14 @@ inline int conv_kernels_init() {
   cudaGetDevice(&dev);
   if (done_for_device == dev) return 0;
   const int rowbs[2] = {128, 64}, mts[3] = {1, 2, 4};
-  for (int r : rowbs)
-    for (int m : mts) {
-      cudaError_t e = cudaFuncSetAttribute(conv_kernel_for(r, m), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-      if (e != cudaSuccess) return fail((int)e, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    }
+  for (int cg = 1; cg <= 2; ++cg)
+    for (int r : rowbs)
+      for (int m : mts) {
+        if (cg == 2 && r == 64) continue;
+        cudaError_t e =
+            cudaFuncSetAttribute(conv_kernel_for(r, m, cg), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+        if (e != cudaSuccess) return fail((int)e, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+      }
   done_for_device = dev;
   return 0;
 }
@@ -163,8 +209,21 @@ inline int conv_kernels_init() {
 inline int launch_conv(const ConvPlan& plan, cudaStream_t st) {
   int rc = conv_kernels_init();
   if (rc) return rc;
-  conv_kernel_for(plan.p.rowb, plan.p.mt)<<<plan.grid, kConvThreads, plan.smem_bytes, st>>>(plan.tm, plan.p);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = plan.grid;
+  cfg.blockDim = dim3(kConvThreads, 1, 1);
+  cfg.dynamicSmemBytes = plan.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan.cg;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_kernel_for(plan.p.rowb, plan.p.mt, plan.cg), plan.tm, plan.tm_w, plan.p);
+  if (e != cudaSuccess) return fail((int)e, std::string("conv_tc launch: ") + cudaGetErrorString(e));
+  e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("conv_tc launch: ") + cudaGetErrorString(e));
   return 0;
 }

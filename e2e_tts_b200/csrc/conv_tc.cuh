@@ -24,6 +24,13 @@
 //                             /3, LeakyReLU, casts (epilogue.cuh)
 // Accumulators are double-buffered in TMEM when 2*MT*nt <= 512 columns, so the epilogue of unit i overlaps
 // the MMAs of unit i+1.
+//
+// CG = 2 runs the pipeline on a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2), for layers with one N tile: each
+// CTA owns its units, its slab panels and its epilogue; one thread of the even CTA issues M = 256 MMAs whose rows
+// 0-127 / 128-255 are the two CTAs' units and whose B operand (the weight tile) is split between them, nt/2 rows
+// each.  Per CTA that halves the weight bytes streamed into shared memory for every unit and the B bytes every MMA
+// reads back - at C = 256 the weight stream alone (1.4 MB per 128-row unit and k = 11) is two thirds of the MMA
+// operand traffic, and shared-memory bandwidth is what bounds these kernels (profiles/r01_experiments_notes.md).
 #pragma once
 #include "epilogue.cuh"
 
@@ -114,9 +121,10 @@ __device__ unsigned int g_trace2[512][24];
 #define E2E_TR2_FLUSH
 #endif
 
-template <int ROWB, int MT>
+template <int ROWB, int MT, int CG>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
+               const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -128,8 +136,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int panel_bytes = p.slab_rows * ROWB;
-  const int tile_bytes = p.nt * ROWB;
+  const int tile_bytes = p.nt * ROWB / CG;  // bytes of one weight tile (one tap of one panel) held by THIS CTA
   const int total_tiles = p.panels * p.taps;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool cta_leader = rank == 0;
+  // units of this CTA: u_n = CG * (cluster + n * n_clusters) + rank, n = 0 .. N-1.  N is the same for both CTAs of
+  // a pair; a unit index >= n_units is a dummy (utterance index >= B: TMA zero-fills, nothing is stored).
+  const int cluster_id = (int)blockIdx.x / CG, n_clusters = (int)gridDim.x / CG;
+  const int n_super = (p.n_units + CG - 1) / CG;
+  const int N = (n_super - cluster_id + n_clusters - 1) / n_clusters;
+  const int u_first = CG * cluster_id + (int)rank, u_step = CG * n_clusters;
 
   uint8_t* slabs = smem;
   uint8_t* ring = slabs + p.panel_slots * panel_bytes;
@@ -158,16 +174,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], kEpiWarps);
+      mbar_init(&acc_empty[i], kEpiWarps * CG);  // (the even CTA's copy collects both CTAs' epilogue warps)
     }
     fence_mbar_init();
   }
   if (warp == 3) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair(tmem_slot, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before_sync();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // the peer's mbarriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) E2E_TR(1);
@@ -179,17 +201,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
       const int boxes = p.slab_rows / p.box_rows;
       uint32_t slot = 0, par = 1;  // ring position; `par` is the parity a fresh/recycled slot is waited on
       UnitIter it;
-      it.init(blockIdx.x, gridDim.x, p.n_tiles, p.tiles_per_b);
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it.next()) {
-        const int b = it.b;
+      it.init(u_first, u_step, p.n_tiles, p.tiles_per_b);
+      for (int n = 0; n < N; ++n, it.next()) {
+        const int b = it.b;  // >= B for a dummy unit: every row is out of bounds and arrives as zeros
         const int t0 = it.tile * (128 * MT);
         for (int pn = 0; pn < p.panels; ++pn) {
           mbar_wait(&panel_empty[slot], par, 0x100 + slot);
-          mbar_arrive_expect_tx(&panel_full[slot], panel_bytes);
+          if (cta_leader) mbar_arrive_expect_tx(&panel_full[slot], panel_bytes * CG);
           uint8_t* dst = slabs + slot * panel_bytes;
-          for (int bx = 0; bx < boxes; ++bx)
-            tma_load_3d(dst + bx * p.box_rows * ROWB, &tm_in, pn * ch_per_panel, t0 - p.hl + bx * p.box_rows, b,
-                        &panel_full[slot]);
+          for (int bx = 0; bx < boxes; ++bx) {
+            if (CG == 2)
+              tma_load_3d_pair(dst + bx * p.box_rows * ROWB, &tm_in, pn * ch_per_panel, t0 - p.hl + bx * p.box_rows, b,
+                               &panel_full[slot]);
+            else
+              tma_load_3d(dst + bx * p.box_rows * ROWB, &tm_in, pn * ch_per_panel, t0 - p.hl + bx * p.box_rows, b,
+                          &panel_full[slot]);
+          }
           if (++slot == (uint32_t)p.panel_slots) {
             slot = 0;
             par ^= 1;
@@ -202,18 +229,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
       // ---------------- weight producer (bulk copies) ----------------
       uint32_t stage = 0, par = 1;
       UnitIter it;
-      it.init(blockIdx.x, gridDim.x, p.n_tiles, p.tiles_per_b);
-      for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, it.next()) {
-        const int nti = it.nti;
+      it.init(u_first, u_step, p.n_tiles, p.tiles_per_b);
+      for (int n = 0; n < N; ++n, it.next()) {
+        const int nti = it.nti;  // (CG == 2: one N tile per layer, both CTAs of the pair share the weight tiles)
         const uint8_t* wsrc = p.w + static_cast<size_t>(nti) * total_tiles * tile_bytes;
         int first = 0;
         for (int c = 0; c < p.n_chunks; ++c, first += p.tiles_per_chunk) {
           mbar_wait(&w_empty[stage], par, 0x200 + stage);
           const int ntile = min(p.tiles_per_chunk, total_tiles - first);
           const uint32_t bytes = ntile * tile_bytes;
-          mbar_arrive_expect_tx(&w_full[stage], bytes);
-          bulk_load_1d(ring + stage * p.stage_bytes, wsrc + static_cast<size_t>(first) * tile_bytes, bytes,
-                       &w_full[stage]);
+          if (CG == 2) {
+            // this CTA's half (nt/2 rows) of every tile of the chunk; the packed image is a [rows][ROWB] matrix
+            if (cta_leader) mbar_arrive_expect_tx(&w_full[stage], bytes * 2);
+            for (int i = 0; i < ntile; ++i)
+              tma_load_2d_pair(ring + stage * p.stage_bytes + i * tile_bytes, &tm_w, 0,
+                               (nti * total_tiles + first + i) * p.nt + (int)rank * (p.nt / 2), &w_full[stage]);
+          } else {
+            mbar_arrive_expect_tx(&w_full[stage], bytes);
+            bulk_load_1d(ring + stage * p.stage_bytes, wsrc + static_cast<size_t>(first) * tile_bytes, bytes,
+                         &w_full[stage]);
+          }
           if (++stage == (uint32_t)p.n_stages) {
             stage = 0;
             par ^= 1;
@@ -221,36 +256,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
         }
       }
     }
-  } else if (warp == 2) {
-    // ---------------- MMA issuer ----------------
+  } else if (warp == 2 && cta_leader) {
+    // ---------------- MMA issuer (even CTA of a pair only) ----------------
     // The whole warp runs the loop (warp-uniform control flow and address arithmetic); one elected lane issues
     // the tcgen05 instructions.  No divisions: ring positions are counters that wrap.
     const bool leader = elect_one();
-    const uint32_t idesc = umma_idesc_bf16(128, p.nt);
+    const uint32_t idesc = umma_idesc_bf16(128 * CG, p.nt);
+    auto wait_full = [&](uint64_t* bar, uint32_t par, uint32_t code) {
+      if (CG == 2) mbar_wait_cluster(bar, par, code);
+      else mbar_wait(bar, par, code);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (CG == 2) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
     const uint32_t slab_lo = ((smem_u32(slabs) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t panel16 = panel_bytes >> 4, stage16 = p.stage_bytes >> 4, tile16 = tile_bytes >> 4;
     uint32_t slot = 0, ppar = 0, stage = 0, wpar = 0, acc = 0, apar = 1;
     bool first_unit = true;
     UnitIter uit;
-    uit.init(blockIdx.x, gridDim.x, p.n_tiles, p.tiles_per_b);
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, uit.next()) {
+    uit.init(u_first, u_step, p.n_tiles, p.tiles_per_b);
+    for (int n = 0; n < N; ++n, uit.next()) {
       const int nti = uit.nti;
-      mbar_wait(&acc_empty[acc], apar, 0x300 + acc);
+      wait_full(&acc_empty[acc], apar, 0x300 + acc);
       tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * (MT * p.nt);
       if (first_unit && leader) E2E_TR(2);
       int tap = 0, left = total_tiles;
       uint32_t accum = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
-        mbar_wait(&w_full[stage], wpar, 0x400 + stage);
+        wait_full(&w_full[stage], wpar, 0x400 + stage);
         tc_fence_after_sync();
         const int ntile = min(p.tiles_per_chunk, left);
         left -= ntile;
         uint32_t b_lo = ring_lo + stage * stage16;
         for (int i = 0; i < ntile; ++i, b_lo += tile16) {
           if (tap == 0) {
-            mbar_wait(&panel_full[slot], ppar, 0x500 + slot);
+            wait_full(&panel_full[slot], ppar, 0x500 + slot);
             tc_fence_after_sync();
           }
           const uint32_t a_lo = slab_lo + slot * panel16 + (p.hl + p.shift[nti][tap]) * ROW16;
@@ -261,16 +304,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
               for (int ks = 0; ks < KS; ++ks) {
                 const uint64_t da = (static_cast<uint64_t>(DESC_HI) << 32) | (a_lo + m * (128 * ROW16) + ks * 2);
                 const uint64_t db = (static_cast<uint64_t>(DESC_HI) << 32) | (b_lo + ks * 2);
-                if (ks == 0)
-                  umma_bf16(d_tmem + m * p.nt, da, db, idesc, accum);
-                else
-                  umma_bf16_acc(d_tmem + m * p.nt, da, db, idesc);
+                if (CG == 2) {
+                  if (ks == 0)
+                    umma_bf16_pair(d_tmem + m * p.nt, da, db, idesc, accum);
+                  else
+                    umma_bf16_acc_pair(d_tmem + m * p.nt, da, db, idesc);
+                } else {
+                  if (ks == 0)
+                    umma_bf16(d_tmem + m * p.nt, da, db, idesc, accum);
+                  else
+                    umma_bf16_acc(d_tmem + m * p.nt, da, db, idesc);
+                }
               }
             }
           }
           accum = 1;
           if (++tap == p.taps) {
-            if (leader) umma_commit(&panel_empty[slot]);  // slab panel consumed: the producer may refill it
+            if (leader) commit(&panel_empty[slot]);  // slab panel consumed: the producers may refill it
             tap = 0;
             if (++slot == (uint32_t)p.panel_slots) {
               slot = 0;
@@ -278,13 +328,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
             }
           }
         }
-        if (leader) umma_commit(&w_empty[stage]);
+        if (leader) commit(&w_empty[stage]);
         if (++stage == (uint32_t)p.n_stages) {
           stage = 0;
           wpar ^= 1;
         }
       }
-      if (leader) umma_commit(&acc_full[acc]);
+      if (leader) commit(&acc_full[acc]);
       if (first_unit && leader) E2E_TR(3);
       first_unit = false;
       if (++acc == (uint32_t)p.n_acc) {
@@ -310,8 +360,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
     eo.inv = p.res_inv_slope;
     uint32_t it = 0, acc = 0, apar = 0;
     UnitIter uit;
-    uit.init(blockIdx.x, gridDim.x, p.n_tiles, p.tiles_per_b);
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x, ++it, uit.next()) {
+    uit.init(u_first, u_step, p.n_tiles, p.tiles_per_b);
+    for (int n = 0; n < N; ++n, ++it, uit.next()) {
       const int nti = uit.nti;
       const int b = uit.b;
       const int t0 = uit.tile * (128 * MT);
@@ -322,7 +372,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
       auto item_off = [&](int item, int& n0, bool& valid) -> size_t {
         const int m = item / nchunk, cc = item - m * nchunk;
         const int t = t0 + m * 128 + row_in_tile;
-        valid = item < items && t < p.T;
+        valid = item < items && t < p.T && b < p.B;
         n0 = nti * p.nt + cc * 16;
         return (static_cast<size_t>(b) * p.T + (valid ? t : 0)) * p.n_total + n0;
       };
@@ -363,7 +413,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
       // all of this warp's TMEM reads of the unit are complete (tcgen05.wait::ld above): release the accumulator
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_remote(&acc_empty[acc], 0);  // the issuing thread waits in the even CTA
+        else mbar_arrive(&acc_empty[acc]);
+      }
       if (it == 0 && threadIdx.x == 128) E2E_TR(6);
       if (++acc == (uint32_t)p.n_acc) {
         acc = 0;
@@ -373,10 +426,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvParams p) {
   }
 
   tc_fence_before_sync();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair's MMAs can still touch it
+  else __syncthreads();
   if (warp == 3) {
     __syncwarp();
-    tmem_dealloc(tmem_base, 512);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
   if (threadIdx.x == 0) E2E_TR(7);
 }

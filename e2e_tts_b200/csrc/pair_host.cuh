@@ -29,22 +29,6 @@ inline int pair_cta_group(int C, int k) {
   return k >= 11 ? 2 : 1;
 }
 
-// 2-D tensor map over a packed weight image: rows of `rowb` bytes, box = half a tile (nt/2 rows), no swizzle (the
-// image already holds the swizzled bytes).
-inline int make_weight_tensor_map(CUtensorMap* tm, const void* base, int rows, int rowb, int box_rows) {
-  PFN_encodeTiled enc = get_encode_fn();
-  if (!enc) return fail(-10, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[2] = {(cuuint64_t)(rowb / 2), (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)rowb};
-  cuuint32_t box[2] = {(cuuint32_t)(rowb / 2), (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(-11, "cuTensorMapEncodeTiled failed for a weight image");
-  return 0;
-}
-
 // The fused pair needs 4 TMEM accumulators of 128*MT x C fp32 (two units in flight x two convs) and two input
 // slabs + two intermediate slabs in shared memory: supported for C in {32, 64, 128} with MT = 128 / C.
 inline bool pair_supported(int C, int k, int d) {

@@ -352,6 +352,8 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
   rc = make_act_tensor_map(&op.plan.tm, in, B, T, s.cin, p.rowb / 2, p.box_rows);
   if (rc) return rc;
   p.w = L.d_w;
+  rc = conv_weight_map(op.plan, L.d_w);
+  if (rc) return rc;
   p.bias = L.d_bias;
   p.res_act = res_act;
   p.res_inv_slope = 10.0f;  // 1 / LRELU_SLOPE: every residual tensor was written with slope 0.1

@@ -60,6 +60,11 @@ static const Cfg kCfgs[] = {
     {"perf c128 k3 d1 act-only", 128, 128, 128, 3, 1, 0, 16, 27584, 2, 0, 0, 0, 0, 1, 0},
     {"perf c128 k7 d3 act-only", 128, 128, 128, 7, 3, 0, 16, 27584, 2, 0, 0, 0, 0, 1, 0},
     {"perf c128 k7 d1 res f32+act", 128, 128, 128, 7, 1, 0, 16, 27584, 2, 1, 0, 0, 1, 1, 0},
+    // stage-0 shapes as the forward plans them (mt = 1)
+    {"perf c256 k3 d1 mt1 res", 256, 256, 256, 3, 1, 0, 16, 3448, 1, 1, 0, 0, 0, 1, 0},
+    {"perf c256 k7 d3 mt1", 256, 256, 256, 7, 3, 0, 16, 3448, 1, 0, 0, 0, 0, 1, 0},
+    {"perf c256 k11 d5 mt1 res sum", 256, 256, 256, 11, 5, 0, 16, 3448, 1, 1, 1, 0, 0, 1, 0},
+    {"c256 k7 d1 mt1 odd units", 256, 256, 256, 7, 1, 0, 3, 300, 1, 1, 0, 0, 1, 1, 0},
 };
 static const int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 
@@ -202,6 +207,11 @@ int main(int argc, char** argv) {
     return 3;
   }
   p.w = dpack;
+  rc = conv_weight_map(plan, dpack);
+  if (rc) {
+    printf("weight tensor map failed: %s\n", last_error().c_str());
+    return 3;
+  }
   p.bias = db;
   p.res_act = dres;
   p.res_inv_slope = 10.0f;
@@ -210,8 +220,8 @@ int main(int argc, char** argv) {
   p.out_act = dact;
   p.slope = 0.1f;
   p.divisor = c.div3 ? 3.0f : 0.f;
-  printf("  plan: grid=%d units=%d smem=%d mt=%d slab_rows=%d box=%d panel_slots=%d stages=%d stage_bytes=%d chunks=%d n_acc=%d hl=%d\n",
-         plan.grid.x, p.n_units, plan.smem_bytes, p.mt, p.slab_rows, p.box_rows, p.panel_slots, p.n_stages,
+  printf("  plan: cg=%d grid=%d units=%d smem=%d mt=%d slab_rows=%d box=%d panel_slots=%d stages=%d stage_bytes=%d chunks=%d n_acc=%d hl=%d\n",
+         plan.cg, plan.grid.x, p.n_units, plan.smem_bytes, p.mt, p.slab_rows, p.box_rows, p.panel_slots, p.n_stages,
          p.stage_bytes, p.n_chunks, p.n_acc, p.hl);
 
   rc = launch_conv(plan, 0);
