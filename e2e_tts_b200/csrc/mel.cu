@@ -8,11 +8,16 @@
 // so the transform is FFT-structured on chip: a CTA stages the audio of 32 consecutive frames in shared memory
 // once (frames overlap 4x), and each group of 64 threads runs a 512-point complex FFT of the even/odd-packed
 // frame as three radix-8 passes held in registers (8 complex values per thread), exchanging through padded,
-// conflict-free shared-memory maps, followed by the real-FFT recombination pass.  The index maps are emulated
-// and checked on the CPU in tests/test_mel_fft_plan.py.  Warp shuffles reduce the frame energy; the mel
-// filterbank is applied in its sparse form (727 non-zeros instead of a dense 80x513 GEMM); outputs are staged
-// so that the global stores of mel[b][m][t0..t0+32) are 128-byte coalesced.
+// conflict-free shared-memory maps, followed by the real-FFT recombination pass, which produces the bins k and
+// 512-k from one pair of loads (X[512-k] = conj(Ze - W^k Zo)) and only the bins the filterbank reads (0..371 for
+// fmax = 8 kHz).  The frame energy sqrt(sum_k mag_k^2) over all 513 bins comes from Parseval's identity on the
+// windowed samples: sum_{k<=512} |X_k|^2 = (1024 sum_n xw_n^2 + X_0^2 + X_512^2) / 2 (shuffle-reduced).  The mel
+// filterbank is applied in its sparse form (727 non-zeros instead of a dense 80x513 GEMM) with the non-zeros
+// split evenly over the 64 threads of a frame (fixed-order partial sums: deterministic); outputs are staged so
+// that the global stores of mel[b][m][t0..t0+32) are 128-byte coalesced.  The index maps are emulated and
+// checked on the CPU in tests/test_mel_fft_plan.py.
 #include <cmath>
+#include <cstring>
 #include <vector>
 #include <cuda_runtime.h>
 #include "../../include/e2e_tts_b200.h"
@@ -32,21 +37,30 @@ constexpr int kThreads = kGroups * 64;
 constexpr int kAudio = (kF - 1) * kHop + kNfft;  // samples staged per CTA
 constexpr int kSx = 576;                  // padded complex exchange buffer (8 rows of 72 / 64 rows of 9)
 constexpr int kMagPad = 528;
+constexpr int kFbPerMax = 17;             // filterbank non-zeros per thread (64 threads: up to 1088 non-zeros)
+constexpr int kFbSplit = 8;               // partial-sum slots per filter (a filter's non-zeros span <= 8 threads)
 
 struct MelParams {
   const float* wav;
   long long ldw, L;
   int B, T, n_mels, nnz;
+  int nb;               // bins the filterbank reads: 1 + last non-zero column of the basis
+  int fb_per;           // filterbank non-zeros per thread (== the kernel's PER)
   float* mel;
   float* energy;
   int* range_flag;
   const float* window;  // [1024] periodic Hann
   const float2* tw;     // [1024] exp(-2 pi i j / 1024)
-  const float* fb_w;    // [nnz] packed filterbank weights
-  const int* fb_lo;     // [n_mels] first bin of each filter
-  const int* fb_cnt;    // [n_mels] bins per filter
-  const int* fb_off;    // [n_mels] offset into fb_w
+  const float2* fb_ent; // [fb_per][64] (weight, bits of (bin | last << 10 | slot << 11)): entry i of thread t.
+                        // `last` = the thread's last non-zero of that filter: the running sum goes to part[slot]
+                        // (slot = mel * kFbSplit + index of the thread among the filter's threads); padding: 0
 };
+
+__device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT: max relative error 2^-23 (PTX ISA)
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -81,6 +95,10 @@ __device__ __forceinline__ void group_sync(int g) {
   asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");
 }
 
+// PER = filterbank non-zeros per thread (odd: the 64 threads of a frame then read `mag` with an odd stride, which
+// spreads them over the shared-memory banks); 13 covers the e2e-tts basis (727 non-zeros), 17 any basis the
+// constructor accepts.
+template <int PER>
 __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* audio = reinterpret_cast<float*>(smem);                    // [kAudio]
@@ -88,12 +106,10 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
   float2* sx = tw_s + 512;                                          // [kGroups][2][kSx]
   float* mag_all = reinterpret_cast<float*>(sx + kGroups * 2 * kSx);  // [kGroups][kMagPad]
   float* out_s = mag_all + kGroups * kMagPad;                       // [n_mels][kF+1]
-  float* energy_s = out_s + p.n_mels * (kF + 1);                    // [kF]
+  float* energy_s = out_s + ((p.n_mels * (kF + 1) + 3) & ~3);       // [kF]
   float* red_s = energy_s + kF;                                     // [kGroups][2]
-  float* fbw_s = red_s + kGroups * 2;                               // [nnz]
-  int* fb_lo_s = reinterpret_cast<int*>(fbw_s + ((p.nnz + 3) & ~3));  // [n_mels]
-  int* fb_cnt_s = fb_lo_s + p.n_mels;
-  int* fb_off_s = fb_cnt_s + p.n_mels;
+  float* part_all = red_s + kGroups * 2;                            // [kGroups][n_mels][kFbSplit]
+  float2* fb_ent_s = reinterpret_cast<float2*>(part_all + kGroups * p.n_mels * kFbSplit);  // [fb_per][64]
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -105,23 +121,40 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
     const float* row = p.wav + (long long)b * p.ldw;
     const long long base = (long long)f0 * kHop - kPad;  // source index of audio[0]
     const int need = (nf - 1) * kHop + kNfft;
-    bool bad = false;
-    for (int i = tid; i < need; i += kThreads) {
-      long long s = base + i;
-      if (s < 0) s = -s;
-      if (s >= p.L) s = 2 * (p.L - 1) - s;
-      const float v = row[s];
-      bad |= !(v >= -1.0f && v <= 1.0f);
-      audio[i] = v;
+    bool bad = false;  // any sample outside [-1, 1] (NaN included), stft.py:56-57
+    if (base >= 0 && base + need <= p.L && ((reinterpret_cast<uintptr_t>(row + base) & 15) == 0)) {
+      // interior CTA, 16-byte aligned: all of a thread's 128-bit loads are issued before the first use
+      const float4* src4 = reinterpret_cast<const float4*>(row + base);
+      float4* dst4 = reinterpret_cast<float4*>(audio);
+      const int n4 = need >> 2;  // need is a multiple of 256
+      constexpr int kIt = (kAudio / 4 + kThreads - 1) / kThreads;
+      float4 v[kIt];
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int i = tid + it * kThreads;
+        v[it] = i < n4 ? __ldg(src4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int i = tid + it * kThreads;
+        bad |= !(fabsf(v[it].x) <= 1.0f) | !(fabsf(v[it].y) <= 1.0f) | !(fabsf(v[it].z) <= 1.0f) |
+               !(fabsf(v[it].w) <= 1.0f);
+        if (i < n4) dst4[i] = v[it];
+      }
+    } else {
+      for (int i = tid; i < need; i += kThreads) {
+        long long s = base + i;
+        if (s < 0) s = -s;
+        if (s >= p.L) s = 2 * (p.L - 1) - s;
+        const float v = row[s];
+        bad |= !(fabsf(v) <= 1.0f);
+        audio[i] = v;
+      }
     }
     if (bad && p.range_flag) atomicOr(p.range_flag, 1);
     for (int i = tid; i < 512; i += kThreads) tw_s[i] = p.tw[i];
-    for (int i = tid; i < p.nnz; i += kThreads) fbw_s[i] = p.fb_w[i];
-    for (int i = tid; i < p.n_mels; i += kThreads) {
-      fb_lo_s[i] = p.fb_lo[i];
-      fb_cnt_s[i] = p.fb_cnt[i];
-      fb_off_s[i] = p.fb_off[i];
-    }
+    for (int i = tid; i < 64 * PER; i += kThreads) fb_ent_s[i] = p.fb_ent[i];
+    for (int i = tid; i < kGroups * p.n_mels * kFbSplit; i += kThreads) part_all[i] = 0.f;  // unused slots stay 0
   }
 
   const int g = tid >> 6;   // FFT group
@@ -130,6 +163,8 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
   float2* S1 = sx + g * 2 * kSx;
   float2* S2 = S1 + kSx;
   float* mag = mag_all + g * kMagPad;
+  float* part = part_all + g * p.n_mels * kFbSplit;
+  const int nb = p.nb;
 
   // per-thread constants: window taps and twiddles of passes 1 and 2
   float w0[8], w1[8];
@@ -147,10 +182,13 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
     float2 a[8];
     // pass 1: thread n2 = t, points z[64 n1 + n2] = (xw[128 n1 + 2 n2], xw[128 n1 + 2 n2 + 1])
     const float2* src = reinterpret_cast<const float2*>(audio + fl * kHop) + t;
+    float e = 0.f;  // sum of the squared windowed samples of this thread
 #pragma unroll
     for (int n1 = 0; n1 < 8; ++n1) {
       const float2 v = src[64 * n1];
       a[n1] = make_float2(v.x * w0[n1], v.y * w1[n1]);
+      e = fmaf(a[n1].x, a[n1].x, e);
+      e = fmaf(a[n1].y, a[n1].y, e);
     }
     dft8(a);
     S1[t] = a[0];
@@ -175,41 +213,67 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
       S1[k + (k >> 3)] = a[d];
     }
     group_sync(g);
-    // real-FFT recombination: thread t owns bins k = t + 64 j
-    float e = 0.f;
+    // real-FFT recombination: thread t owns the bin pairs (k, 512 - k), k = t + 64 j, j = 0..3; thread 0 also
+    // bin 256.  Ze = (Z[k] + conj Z[512-k]) / 2, Zo = (Z[k] - conj Z[512-k]) / (2i), X[k] = Ze + W^k Zo,
+    // X[512-k] = conj(Ze - W^k Zo).  k = 0 gives the purely real X[0] and X[512].
+    float x0sq = 0.f, xnsq = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 4; ++j) {
       const int k = t + 64 * j;
       const int kk = (512 - k) & 511;
       const float2 za = S1[k + (k >> 3)];
       const float2 zb = S1[kk + (kk >> 3)];
-      // Ze = (Z[k] + conj Z[N-k]) / 2 ; Zo = (Z[k] - conj Z[N-k]) / (2i)
       const float2 ze = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
       const float2 zo = make_float2(0.5f * (za.y + zb.y), -0.5f * (za.x - zb.x));
-      const float2 x = cadd(ze, cmul(tw_s[k], zo));
+      const float2 wz = cmul(tw_s[k], zo);
+      const float2 x = cadd(ze, wz), xp = csub(ze, wz);
       const float s = x.x * x.x + x.y * x.y + 1e-9f;  // stft.py:77
-      mag[k] = sqrtf(s);
-      e += s;
-      if (k == 0) {  // Nyquist bin: X[512] = Ze[0] - Zo[0] (purely real)
-        const float xn = ze.x - zo.x;
-        const float sn = xn * xn + 1e-9f;
-        mag[512] = sqrtf(sn);
-        e += sn;
+      const float sp = xp.x * xp.x + xp.y * xp.y + 1e-9f;
+      if (k < nb) mag[k] = sqrt_approx(s);
+      if (512 - k < nb) mag[512 - k] = sqrt_approx(sp);
+      if (k == 0) {
+        x0sq = x.x * x.x;
+        xnsq = xp.x * xp.x;
       }
     }
+    if (t == 0 && 256 < nb) {
+      const float2 z = S1[256 + 32];
+      mag[256] = sqrt_approx(z.x * z.x + z.y * z.y + 1e-9f);
+    }
+    // energy^2 = sum_{k=0..512} (|X_k|^2 + 1e-9) = (1024 sum xw^2 + X_0^2 + X_512^2) / 2 + 513e-9   (stft.py:84)
+    e = fmaf(1024.f, e, x0sq + xnsq);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if ((t & 31) == 0) red_s[g * 2 + (t >> 5)] = e;
     group_sync(g);
-    // sparse mel filterbank + log compression (stft.py:80-81, utils.py:28)
-    for (int m = t; m < p.n_mels; m += 64) {
-      const int lo_bin = fb_lo_s[m], cnt = fb_cnt_s[m];
-      const float* w = fbw_s + fb_off_s[m];
+    // sparse mel filterbank (stft.py:80): thread t multiplies its fb_per consecutive non-zeros; whenever it finishes
+    // a filter, the running sum goes to that filter's slot of this thread (branch-free: predicated store + select)
+    {
+      // all entry loads, then all magnitude loads, are issued before the (serial) multiply-add chain
+      float2 en[PER];
+      float mv[PER];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) en[i] = fb_ent_s[i * 64 + t];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) mv[i] = mag[__float_as_int(en[i].y) & 0x3ff];
       float acc = 0.f;
-      for (int i = 0; i < cnt; ++i) acc = fmaf(w[i], mag[lo_bin + i], acc);
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int code = __float_as_int(en[i].y);
+        acc = fmaf(en[i].x, mv[i], acc);
+        if (code & 0x400) part[code >> 11] = acc;
+        acc = (code & 0x400) ? 0.f : acc;
+      }
+    }
+    if (t == 0) energy_s[fl] = sqrtf(0.5f * (red_s[g * 2] + red_s[g * 2 + 1]) + 513e-9f);
+    group_sync(g);
+    // fixed-order sum of the partials + log compression (stft.py:81, utils.py:28)
+    for (int m = t; m < p.n_mels; m += 64) {
+      const float4 q0 = *reinterpret_cast<const float4*>(part + m * kFbSplit);
+      const float4 q1 = *reinterpret_cast<const float4*>(part + m * kFbSplit + 4);
+      const float acc = ((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w));
       out_s[m * (kF + 1) + fl] = logf(fmaxf(acc, 1e-5f));
     }
-    if (t == 0) energy_s[fl] = sqrtf(red_s[g * 2] + red_s[g * 2 + 1]);  // stft.py:84
   }
   __syncthreads();
 
@@ -225,12 +289,10 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
 
 struct e2e_mel {
   int n_fft, hop, win, n_mels, nnz;
+  int nb = 0, fb_per = 1;
   float* d_window = nullptr;
   float2* d_tw = nullptr;
-  float* d_fbw = nullptr;
-  int* d_lo = nullptr;
-  int* d_cnt = nullptr;
-  int* d_off = nullptr;
+  float2* d_ent = nullptr;
   int smem_bytes = 0;
 };
 
@@ -240,28 +302,45 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
   if (n_fft != kNfft || win_length != kNfft || hop_length != kHop)
     return fail(-4, "mel front-end supports n_fft == win_length == 1024 and hop_length == 256 (the e2e-tts config)");
   if (n_mels < 1 || n_mels > 128) return fail(-4, "n_mels must be in [1, 128]");
+  // sparse filterbank: the non-zeros in (filter, bin) order, cut into 64 equal runs (one per thread of a frame)
+  struct Ent { float w; int mel, bin; };
+  std::vector<Ent> ents;
+  int nb = 1;
+  for (int r = 0; r < n_mels; ++r)
+    for (int k = 0; k < kBins; ++k) {
+      const float w = mel_basis[(size_t)r * kBins + k];
+      if (w != 0.f) {
+        ents.push_back({w, r, k});
+        nb = k + 1 > nb ? k + 1 : nb;
+      }
+    }
+  const int nnz = (int)ents.size();
+  if (nnz > 64 * kFbPerMax) return fail(-4, "mel filterbank too dense (more than 1088 non-zeros)");
+  const int per = nnz <= 64 * 13 ? 13 : kFbPerMax;  // the two instantiations of mel_kernel
+  // entry i of thread t = non-zero number t * per + i, stored [i][t] (conflict-free for the 64 threads)
+  std::vector<float2> packed((size_t)64 * per, make_float2(0.f, 0.f));
+  std::vector<int> first(n_mels, -1);
+  for (int idx = 0; idx < nnz; ++idx) {
+    const Ent& en = ents[idx];
+    const int t = idx / per, i = idx % per;
+    if (first[en.mel] < 0) first[en.mel] = t;
+    const int q = t - first[en.mel];
+    if (q >= kFbSplit) return fail(-4, "mel filterbank has a filter wider than the kernel's split (8 x per-thread run)");
+    // last non-zero of this filter held by thread t?
+    const bool last = idx + 1 == nnz || ents[idx + 1].mel != en.mel || (idx + 1) / per != t;
+    const int code = en.bin | (last ? 0x400 : 0) | ((en.mel * kFbSplit + q) << 11);
+    float cf;
+    memcpy(&cf, &code, 4);
+    packed[(size_t)i * 64 + t] = make_float2(en.w, cf);
+  }
   e2e_mel* m = new e2e_mel;
   m->n_fft = n_fft;
   m->hop = hop_length;
   m->win = win_length;
   m->n_mels = n_mels;
-  std::vector<float> w;
-  std::vector<int> lo(n_mels), cnt(n_mels), off(n_mels);
-  for (int r = 0; r < n_mels; ++r) {
-    const float* row = mel_basis + (size_t)r * kBins;
-    int first = -1, last = -1;
-    for (int k = 0; k < kBins; ++k)
-      if (row[k] != 0.f) {
-        if (first < 0) first = k;
-        last = k;
-      }
-    lo[r] = first < 0 ? 0 : first;
-    cnt[r] = first < 0 ? 0 : last - first + 1;
-    off[r] = (int)w.size();
-    for (int k = 0; k < cnt[r]; ++k) w.push_back(row[lo[r] + k]);
-  }
-  m->nnz = (int)w.size();
-  if (w.empty()) w.push_back(0.f);
+  m->nnz = nnz;
+  m->nb = nb;
+  m->fb_per = per;
   std::vector<float> window(kNfft);
   std::vector<float2> tw(kNfft);
   const double pi = 3.14159265358979323846;
@@ -269,8 +348,9 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
     window[n] = (float)(0.5 - 0.5 * cos(2.0 * pi * n / kNfft));  // periodic Hann, stft.py:44
     tw[n] = make_float2((float)cos(2.0 * pi * n / kNfft), (float)(-sin(2.0 * pi * n / kNfft)));
   }
-  m->smem_bytes = (kAudio + 2 * 512 + kGroups * 2 * kSx * 2 + kGroups * kMagPad + n_mels * (kF + 1) + kF +
-                   kGroups * 2 + ((m->nnz + 3) & ~3) + 3 * n_mels) * 4;
+  // mirrors the carve-up at the top of mel_kernel
+  m->smem_bytes = (kAudio + 2 * 512 + kGroups * 2 * kSx * 2 + kGroups * kMagPad + ((n_mels * (kF + 1) + 3) & ~3) + kF +
+                   kGroups * 2 + kGroups * n_mels * kFbSplit + 2 * 64 * per) * 4;
   if (m->smem_bytes > 113 * 1024) {
     delete m;
     return fail(-4, "mel filterbank too dense for the shared-memory budget");
@@ -283,12 +363,10 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
   };
   up((void**)&m->d_window, window.data(), window.size() * 4);
   up((void**)&m->d_tw, tw.data(), tw.size() * 8);
-  up((void**)&m->d_fbw, w.data(), w.size() * 4);
-  up((void**)&m->d_lo, lo.data(), lo.size() * 4);
-  up((void**)&m->d_cnt, cnt.data(), cnt.size() * 4);
-  up((void**)&m->d_off, off.data(), off.size() * 4);
+  up((void**)&m->d_ent, packed.data(), packed.size() * 8);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
+    e = cudaFuncSetAttribute(per == 13 ? mel_kernel<13> : mel_kernel<kFbPerMax>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
   if (e != cudaSuccess) {
     e2e_mel_destroy(m);
     return fail((int)e, std::string("e2e_mel_create: ") + cudaGetErrorString(e));
@@ -301,10 +379,7 @@ extern "C" void e2e_mel_destroy(e2e_mel* m) {
   if (!m) return;
   cudaFree(m->d_window);
   cudaFree(m->d_tw);
-  cudaFree(m->d_fbw);
-  cudaFree(m->d_lo);
-  cudaFree(m->d_cnt);
-  cudaFree(m->d_off);
+  cudaFree(m->d_ent);
   delete m;
 }
 
@@ -330,17 +405,19 @@ extern "C" int e2e_mel_forward(e2e_mel* m, const float* wav, int32_t B, int64_t 
   p.T = (int)T;
   p.n_mels = m->n_mels;
   p.nnz = m->nnz;
+  p.nb = m->nb;
+  p.fb_per = m->fb_per;
   p.mel = mel;
   p.energy = energy;
   p.range_flag = range_flag;
   p.window = m->d_window;
   p.tw = m->d_tw;
-  p.fb_w = m->d_fbw;
-  p.fb_lo = m->d_lo;
-  p.fb_cnt = m->d_cnt;
-  p.fb_off = m->d_off;
+  p.fb_ent = m->d_ent;
   dim3 grid((unsigned)((T + kF - 1) / kF), (unsigned)B);
-  mel_kernel<<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  if (m->fb_per == 13)
+    mel_kernel<13><<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  else
+    mel_kernel<kFbPerMax><<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("mel_kernel launch: ") + cudaGetErrorString(e));
   return 0;

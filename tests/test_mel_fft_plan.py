@@ -47,15 +47,17 @@ def kernel_fft1024_real(xw):
             k = k1 + 8 * c + 64 * d
             S3[k + (k >> 3)] = v[d]
     X = np.zeros(513, complex)
-    for t in range(64):                                                    # post pass: thread t, bins t + 64 j
-        for j in range(8):
+    for t in range(64):                                # post pass: thread t, bin pairs (k, 512 - k), k = t + 64 j
+        for j in range(4):
             k = t + 64 * j
             kk = (512 - k) % 512
             a, bq = S3[k + (k >> 3)], np.conj(S3[kk + (kk >> 3)])
             ze, zo = (a + bq) / 2, (a - bq) / 2j
-            X[k] = ze + tw[k] * zo
-            if k == 0:
-                X[512] = ze - zo
+            wz = tw[k] * zo
+            X[k] = ze + wz
+            X[512 - k] = np.conj(ze - wz)
+    z = S3[256 + 32]                                   # thread 0: bin 256 (only |X| is used by the kernel)
+    X[256] = np.conj(z)
     return X
 
 
@@ -78,3 +80,38 @@ def test_smem_maps_are_injective():
     s3 = {k + (k >> 3) for k in range(512)}
     assert len(s1) == 512 and len(s2) == 512 and len(s3) == 512
     assert max(s1) < 576 and max(s2) < 576 and max(s3) < 576
+
+
+def test_parseval_energy_identity():
+    """mel.cu computes sum_{k<=512} |X_k|^2 as (1024 * sum xw^2 + X_0^2 + X_512^2) / 2 (stft.py:84 sums the bins)."""
+    rng = np.random.default_rng(2)
+    for _ in range(3):
+        x = rng.uniform(-1, 1, 1024) * (0.5 - 0.5 * np.cos(2 * np.pi * np.arange(1024) / 1024))
+        X = np.fft.rfft(x)
+        lhs = (np.abs(X) ** 2).sum()
+        rhs = 0.5 * (1024.0 * (x ** 2).sum() + X[0].real ** 2 + X[512].real ** 2)
+        np.testing.assert_allclose(lhs, rhs, rtol=1e-12)
+
+
+def test_filterbank_split_is_exact_and_bounded():
+    """Mirror of e2e_mel_create's sparse filterbank split (mel.cu): the non-zeros in (filter, bin) order are cut
+    into 64 runs of PER entries; every thread leaves one partial per filter it touched; fixed-order sums reproduce
+    basis @ mag, and no filter spreads over more than kFbSplit = 8 threads."""
+    from oracle import mel_oracle as mo
+    basis = mo.slaney_mel_basis().astype(np.float64)
+    n_mels = basis.shape[0]
+    ents = [(basis[r, k], r, k) for r in range(n_mels) for k in range(basis.shape[1]) if basis[r, k] != 0.0]
+    assert len(ents) <= 64 * 17
+    per = 13 if len(ents) <= 64 * 13 else 17            # the two instantiations of mel_kernel<PER>
+    rng = np.random.default_rng(3)
+    mag = rng.uniform(0, 10, basis.shape[1])
+    first, nthr, part = {}, {}, {}
+    for t in range(64):
+        for (w, r, k) in ents[t * per:(t + 1) * per]:
+            first.setdefault(r, t)
+            nthr[r] = t - first[r] + 1
+            part[(r, t - first[r])] = part.get((r, t - first[r]), 0.0) + w * mag[k]
+    assert max(nthr.values()) <= 8
+    got = np.array([sum(part[(r, q)] for q in range(nthr[r])) for r in range(n_mels)])
+    np.testing.assert_allclose(got, basis @ mag, rtol=1e-12)
+    assert 1 + max(k for (_, _, k) in ents) == 372          # bins the kernel computes magnitudes for
