@@ -37,6 +37,8 @@ SYMBOLS = {
     "e2e_voc_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
     "e2e_voc_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                 c_void_p, c_size_t, c_void_p]),
+    "e2e_voc_forward_pcm16": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p,
+                                      c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "e2e_voc_set_profile_events": (c_int, [c_void_p, c_void_p, c_void_p]),
     "e2e_voc_hop": (c_int, [c_void_p]),
     "e2e_voc_launches_per_forward": (c_int, [c_void_p]),

@@ -4,7 +4,10 @@
 //                    -> channels-last bf16 [B][T][cin_pad] operand of conv_pre (padding channels = 0)
 //   * post_conv_tanh: conv_post (Conv1d C->1, k=7, pad 3) + tanh  (generator.py:50-51).  Its input is the
 //                    previous epilogue's leaky_relu(x, 0.01) in bf16 (generator.py:49), N = 1 so this is a
-//                    224-term dot product per sample, bandwidth-shaped.
+//                    224-term dot product per sample, bandwidth-shaped.  Output: fp32 waveform (the reference's
+//                    return value), or - PostOut::pcm - the int16 PCM its caller makes of it (combine_audio,
+//                    src/api/utils.py:108-117: trim to mel_len * hop, * max_wav_value, astype int16), which halves
+//                    the device->host and gather bytes.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -33,6 +36,22 @@ __global__ void mel_to_act_kernel(const float* __restrict__ mel, long long sB, l
   *reinterpret_cast<uint4*>(out + ((long long)b * T + t) * cpad + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
+// Where post_conv_tanh writes.  pcm == nullptr: wav[b][t] = tanh(.) fp32.  Otherwise pcm[b][t] =
+// (int16) trunc(tanh(.) * scale) for t < lens[b] * hop (all t when lens == nullptr) and 0 beyond: numpy's
+// astype("int16") truncates toward zero; exactly +1.0 * 32768 saturates to 32767 instead of wrapping.
+struct PostOut {
+  float* wav;
+  int16_t* pcm;
+  const int32_t* lens;  // device [B] mel frames per utterance, or nullptr
+  int hop;
+  float scale;
+};
+
+__device__ __forceinline__ int16_t to_pcm16(float y, float scale) {
+  const int v = __float2int_rz(y * scale);
+  return (int16_t)max(-32768, min(32767, v));
+}
+
 constexpr int kPostMaxW = 7 * 64;
 constexpr int kPostTile = 512;  // output samples per block (2 per thread)
 
@@ -42,7 +61,7 @@ constexpr int kPostTile = 512;  // output samples per block (2 per thread)
 template <int C, int K>
 __global__ void __launch_bounds__(256)
 post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, float bias, int B, int T,
-                      float* __restrict__ wav) {
+                      const PostOut out) {
   constexpr int HALF = (K - 1) / 2;
   constexpr int ROWS = kPostTile + 2 * HALF;
   constexpr int ROW16 = C / 8;       // uint4 per row
@@ -84,7 +103,20 @@ post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const float* __rest
     }
   }
   const int t = t0 + o;
-  float* dst = wav + (long long)b * T + t;
+  if (out.pcm) {
+    const long long valid = out.lens ? (long long)out.lens[b] * out.hop : (long long)T;
+    int16_t* dst = out.pcm + (long long)b * T + t;
+    const int16_t s0 = t < valid ? to_pcm16(tanhf(acc0), out.scale) : (int16_t)0;
+    const int16_t s1 = t + 1 < valid ? to_pcm16(tanhf(acc1), out.scale) : (int16_t)0;
+    if (t + 1 < T && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+      *reinterpret_cast<uint32_t*>(dst) = (uint32_t)(uint16_t)s0 | ((uint32_t)(uint16_t)s1 << 16);
+    } else {
+      if (t < T) dst[0] = s0;
+      if (t + 1 < T) dst[1] = s1;
+    }
+    return;
+  }
+  float* dst = out.wav + (long long)b * T + t;
   if (t + 1 < T && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
     *reinterpret_cast<float2*>(dst) = make_float2(tanhf(acc0), tanhf(acc1));
   } else {
@@ -96,7 +128,7 @@ post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const float* __rest
 // Generic fallback (any C multiple of 8, any odd k): one output per thread, rows read through L1.
 __global__ void __launch_bounds__(256)
 post_conv_tanh_generic_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, float bias, int B,
-                              int T, int C, int k, float* __restrict__ wav) {
+                              int T, int C, int k, const PostOut out) {
   __shared__ float sw[kPostMaxW];
   for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -120,7 +152,12 @@ post_conv_tanh_generic_kernel(const __nv_bfloat16* __restrict__ act, const float
       }
     }
   }
-  wav[(long long)b * T + t] = tanhf(acc);
+  if (out.pcm) {
+    const long long valid = out.lens ? (long long)out.lens[b] * out.hop : (long long)T;
+    out.pcm[(long long)b * T + t] = t < valid ? to_pcm16(tanhf(acc), out.scale) : (int16_t)0;
+  } else {
+    out.wav[(long long)b * T + t] = tanhf(acc);
+  }
 }
 
 }  // namespace e2e

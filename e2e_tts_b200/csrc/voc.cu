@@ -497,9 +497,9 @@ extern "C" int e2e_voc_launches_per_forward(const e2e_voc* v) {
   return n;
 }
 
-extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B,
-                               int32_t T, float* wav, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!v || !mel || !wav || !workspace) return fail(-1, "null argument");
+static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B, int32_t T,
+                            const PostOut& post, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!v || !mel || (!post.wav && !post.pcm) || !workspace) return fail(-1, "null argument");
   if (B < 1 || T < 1) return fail(-1, "B and T must be positive");
   if (e2e_voc_missing_layers(v) != 0) return fail(-7, "e2e_voc_forward before all layers were loaded");
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(-1, "workspace must be 1024-byte aligned");
@@ -543,11 +543,11 @@ extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t
       if (L.cin == 32 && L.k == 7) {
         dim3 grid((Tout + kPostTile - 1) / kPostTile, B);
         post_conv_tanh_kernel<32, 7><<<grid, 256, 0, st>>>(bf.Y, reinterpret_cast<const float*>(L.d_w), L.post_bias, B,
-                                                           Tout, wav);
+                                                           Tout, post);
       } else {
         dim3 grid((Tout + 255) / 256, B);
         post_conv_tanh_generic_kernel<<<grid, 256, 0, st>>>(bf.Y, reinterpret_cast<const float*>(L.d_w), L.post_bias,
-                                                            B, Tout, L.cin, L.k, wav);
+                                                            B, Tout, L.cin, L.k, post);
       }
     }
     if (oi == last_conv && v->ev_end) cudaEventRecord(v->ev_end, st);
@@ -557,6 +557,22 @@ extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("e2e_voc_forward launch: ") + cudaGetErrorString(e));
   return 0;
+}
+
+extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B,
+                               int32_t T, float* wav, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!wav) return fail(-1, "null argument");
+  PostOut post{wav, nullptr, nullptr, v ? v->hop : 1, 1.0f};
+  return voc_forward_impl(v, mel, sB, sC, sT, B, T, post, workspace, workspace_bytes, stream);
+}
+
+extern "C" int e2e_voc_forward_pcm16(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B,
+                                     int32_t T, const int32_t* mel_lengths, float max_wav_value, int16_t* pcm,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  if (!pcm) return fail(-1, "null argument");
+  if (!(max_wav_value > 0.f) || max_wav_value > 32768.f) return fail(-1, "max_wav_value must be in (0, 32768]");
+  PostOut post{nullptr, pcm, mel_lengths, v ? v->hop : 1, max_wav_value};
+  return voc_forward_impl(v, mel, sB, sC, sT, B, T, post, workspace, workspace_bytes, stream);
 }
 
 extern "C" const char* e2e_last_error_string(void) { return last_error().c_str(); }

@@ -22,13 +22,14 @@ def shard_bounds(n: int, world_size: int, rank: int) -> Tuple[int, int]:
 
 def synthesize_shard(vocoder: Callable[[torch.Tensor], torch.Tensor], mel_local: torch.Tensor) -> torch.Tensor:
     """Local part: mel [b, 80, T] -> wav [b, hop*T] (the `.squeeze(1)` of utils.py:144)."""
-    if mel_local.shape[0] == 0:  # this rank owns no utterance (B < world size)
-        hop = getattr(vocoder, "hop", None)
-        if hop is None:
-            hop = vocoder(mel_local.new_zeros((1,) + tuple(mel_local.shape[1:]))).shape[-1] // mel_local.shape[-1]
-        return mel_local.new_zeros((0, hop * mel_local.shape[-1]))
+    if mel_local.shape[0] == 0:  # this rank owns no utterance (B < world size): one dummy call fixes shape and dtype
+        with torch.no_grad():
+            probe = vocoder(mel_local.new_zeros((1,) + tuple(mel_local.shape[1:])))
+        probe = probe.squeeze(1) if probe.dim() == 3 else probe
+        return probe.new_zeros((0, probe.shape[-1]))
     with torch.no_grad():
-        return vocoder(mel_local).squeeze(1)
+        wav = vocoder(mel_local)
+    return wav.squeeze(1) if wav.dim() == 3 else wav  # [b,1,S] fp32 (forward) or [b,S] int16 (forward_pcm16)
 
 
 def gather_waveforms(wav_local: torch.Tensor, total: int, dst: int = 0,
@@ -50,10 +51,13 @@ def gather_waveforms(wav_local: torch.Tensor, total: int, dst: int = 0,
     if send.shape[0] != bmax:
         send = torch.cat([wav_local, wav_local.new_zeros((bmax - wav_local.shape[0], S))], 0)
     send = send.contiguous()
+    dtype = send.dtype
+    if dtype == torch.int16:  # NCCL has no int16: int16 PCM (HifiGan.forward_pcm16) travels as bytes
+        send = send.view(torch.uint8)
     if rank == dst:
         recv: List[torch.Tensor] = [torch.empty_like(send) for _ in range(world)]
         dist.gather(send, recv, dst=dst, group=group)
-        return torch.cat([recv[r][:counts[r]] for r in range(world)], 0)
+        return torch.cat([recv[r].view(dtype)[:counts[r]] for r in range(world)], 0)
     dist.gather(send, None, dst=dst, group=group)
     return None
 

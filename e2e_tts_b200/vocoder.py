@@ -260,8 +260,7 @@ class HifiGan(nn.Module):
             self._workspaces[key] = ws
         return ws
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """generator.py:37-53.  x: [B, 80, T] float32 CUDA tensor (non-contiguous views are fine)."""
+    def _check_input(self, x: torch.Tensor) -> None:
         if not isinstance(x, torch.Tensor) or x.dim() != 3 or x.shape[1] != self.in_channels:
             raise ValueError("expected a [B, %d, T] tensor, got %s" % (self.in_channels, tuple(getattr(x, "shape", ()))))
         if not x.is_cuda:
@@ -271,12 +270,16 @@ class HifiGan(nn.Module):
             raise ValueError("expected float32 input, got %s" % x.dtype)
         if torch.is_grad_enabled() and x.requires_grad:
             raise RuntimeError("e2e_tts_b200.HifiGan is inference-only; call it under torch.no_grad()")
-        B, _, T = x.shape
-        if B == 0 or T == 0:
-            return x.new_zeros((B, 1, self.hop * T))
         p0 = next(self.parameters())
         if p0.device != x.device:
             raise RuntimeError("module parameters are on %s but the input is on %s" % (p0.device, x.device))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """generator.py:37-53.  x: [B, 80, T] float32 CUDA tensor (non-contiguous views are fine)."""
+        self._check_input(x)
+        B, _, T = x.shape
+        if B == 0 or T == 0:
+            return x.new_zeros((B, 1, self.hop * T))
         with torch.cuda.device(x.device):
             self._sync_native(x.device)
             ws = self._workspace(B, T, x.device)
@@ -292,6 +295,32 @@ class HifiGan(nn.Module):
                                                B, T, out.data_ptr(), ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()),
                                                stream)
             _native.check(rc, "e2e_voc_forward")
+        return out
+
+    def forward_pcm16(self, x: torch.Tensor, mel_lengths=None, max_wav_value: float = 32768.0) -> torch.Tensor:
+        """forward() fused with the caller's post-processing (combine_audio, e2e_tts/src/api/utils.py:108-117):
+        returns int16 PCM [B, hop*T] = trunc(wav * max_wav_value), zero beyond mel_lengths[b] * hop.  Half the
+        device->host (and multi-GPU gather) bytes of forward().  mel_lengths: None, a sequence, or an int tensor [B]."""
+        self._check_input(x)
+        B, _, T = x.shape
+        if B == 0 or T == 0:
+            return torch.zeros((B, self.hop * T), dtype=torch.int16, device=x.device)
+        lens = None
+        if mel_lengths is not None:
+            lens = torch.as_tensor(mel_lengths).to(device=x.device, dtype=torch.int32).contiguous()
+            if lens.shape != (B,):
+                raise ValueError("mel_lengths must have shape [%d], got %s" % (B, tuple(lens.shape)))
+        with torch.cuda.device(x.device):
+            self._sync_native(x.device)
+            ws = self._workspace(B, T, x.device)
+            ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+            out = torch.empty((B, self.hop * T), dtype=torch.int16, device=x.device)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            rc = _native.lib().e2e_voc_forward_pcm16(self._handle, x.data_ptr(), x.stride(0), x.stride(1), x.stride(2),
+                                                     B, T, lens.data_ptr() if lens is not None else None,
+                                                     float(max_wav_value), out.data_ptr(), ws_ptr,
+                                                     ws.numel() - (ws_ptr - ws.data_ptr()), stream)
+            _native.check(rc, "e2e_voc_forward_pcm16")
         return out
 
     def __del__(self):

@@ -69,6 +69,15 @@ size_t e2e_voc_workspace_bytes(const e2e_voc* v, int32_t B, int32_t T);
 int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B, int32_t T,
                     float* wav, void* workspace, size_t workspace_bytes, void* stream);
 
+/* e2e_voc_forward fused with the caller's post-processing (combine_audio, e2e_tts/src/api/utils.py:108-117:
+ * `audio[: mel_len * hop] * max_wav_value` ... `.astype("int16")`): pcm: device int16 [B][upsample*T];
+ * pcm[b][t] = (int16) trunc(wav[b][t] * max_wav_value) for t < mel_lengths[b] * upsample, 0 beyond.  mel_lengths:
+ * device int32 [B] or NULL (= every utterance has T frames).  Truncation toward zero like numpy's astype; a sample
+ * of exactly +1.0 saturates to 32767 (numpy wraps it).  Halves the device->host and multi-GPU gather bytes. */
+int e2e_voc_forward_pcm16(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B, int32_t T,
+                          const int32_t* mel_lengths, float max_wav_value, int16_t* pcm, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* Measurement hook: the NEXT e2e_voc_forward records `ev_begin` (a cudaEvent_t) on its stream just before its first
  * tensor-core convolution launch and `ev_end` right after its last one, then forgets both (one-shot).  bench.py
  * uses it to time the dominant kernel family inside the timed region.  Pass NULLs to cancel. */

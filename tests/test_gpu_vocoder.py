@@ -121,3 +121,26 @@ def test_weights_reload_after_in_place_update():
         want = ho.hifigan_forward(sd2, cfg, mel.cpu())
     assert not torch.equal(a, b)
     check(b, want, "reloaded")
+
+
+def test_forward_pcm16_is_the_callers_post_processing_fused():
+    """HifiGan.forward_pcm16 == combine_audio's trim / * max_wav_value / astype(int16) (src/api/utils.py:108-117)
+    applied to forward(): same kernel arithmetic, so the int16 stream must be bit-identical."""
+    from oracle import postprocess_oracle as po
+    voc, _ = build(ho.DEFAULT_CONFIG, 11, "strong")
+    mel = mel_like(3, 40, 21).cuda()
+    lengths = [40, 17, 0]
+    with torch.no_grad():
+        wav = voc(mel).squeeze(1)
+        pcm = voc.forward_pcm16(mel, lengths)
+        pcm_full = voc.forward_pcm16(mel)
+    assert pcm.dtype == torch.int16 and pcm.shape == wav.shape
+    want_full = torch.trunc(wav * 32768.0).clamp(-32768, 32767).to(torch.int16)
+    assert torch.equal(pcm_full, want_full)
+    for b, n in enumerate(lengths):
+        assert torch.equal(pcm[b, : n * 256], want_full[b, : n * 256])
+        assert int(pcm[b, n * 256:].abs().max().item()) == 0 if n < 40 else True
+    ref_stream = po.combine_audio(list(wav.cpu().numpy()), lengths, 100)
+    assert np.array_equal(pkg.combine_audio(list(pcm.cpu()), lengths, 100), ref_stream)
+    with pytest.raises(ValueError):
+        voc.forward_pcm16(mel, [1, 2])

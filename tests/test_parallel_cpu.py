@@ -30,16 +30,24 @@ class FakeVocoder:
         return mel.sum(1, keepdim=True).repeat_interleave(self.hop, dim=2) + 1.0
 
 
-def _worker(rank, world, port, B, T, q):
+class FakePcmVocoder(FakeVocoder):
+    """Stand-in for HifiGan.forward_pcm16: int16 [b, hop*T] (exercises the byte-view gather, NCCL has no int16)."""
+
+    def __call__(self, mel):
+        return (super().__call__(mel).squeeze(1) * 100).to(torch.int16)
+
+
+def _worker(rank, world, port, B, T, q, pcm=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         g = torch.Generator().manual_seed(5)
         mel = torch.randn(B, 80, T, generator=g)
-        out = parallel.synthesize_sharded(FakeVocoder(), mel, dst=0)
+        voc = FakePcmVocoder() if pcm else FakeVocoder()
+        out = parallel.synthesize_sharded(voc, mel, dst=0)
         if rank == 0:
-            want = FakeVocoder()(mel).squeeze(1)
+            want = voc(mel) if pcm else voc(mel).squeeze(1)
             q.put(bool(out is not None and out.shape == want.shape and torch.equal(out, want)))
         else:
             q.put(out is None)
@@ -47,15 +55,15 @@ def _worker(rank, world, port, B, T, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("B", [6, 5, 1])
-def test_sharded_synthesis_gathers_on_rank0_gloo_world2(B):
+@pytest.mark.parametrize("B,pcm", [(6, False), (5, False), (1, False), (5, True), (1, True)])
+def test_sharded_synthesis_gathers_on_rank0_gloo_world2(B, pcm):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, 7, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, 7, q, pcm)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in procs]
