@@ -4,11 +4,12 @@ Drop-in names (same signatures as the reference, see each module's docstring):
     HifiGan, ResBlock1, ResBlock2, get_padding, init_weights   <- e2e_tts/models/vocoder/{generator,layers,function}.py
     TorchSTFT, generate_melspecs, dynamic_range_compression     <- e2e_tts/src/tools/{stft,utils}.py
     combine_audio                                               <- e2e_tts/src/api/utils.py:108-117 (+ HifiGan.forward_pcm16)
+    iSTFT, inverse_stft                                         <- generator.py:65-119, e2e_tts/src/tools/stft.py:138-148
 """
-from .vocoder import HifiGan, ResBlock1, ResBlock2, get_padding, init_weights, LRELU_SLOPE  # noqa: F401
-from .stft import TorchSTFT, generate_melspecs, dynamic_range_compression, dynamic_range_decompression  # noqa: F401
+from .vocoder import HifiGan, iSTFT, ResBlock1, ResBlock2, get_padding, init_weights, LRELU_SLOPE  # noqa: F401
+from .stft import TorchSTFT, generate_melspecs, inverse_stft, dynamic_range_compression, dynamic_range_decompression  # noqa: F401
 
 from .postprocess import combine_audio  # noqa: F401
 
-__all__ = ["combine_audio", "HifiGan", "ResBlock1", "ResBlock2", "get_padding", "init_weights", "TorchSTFT", "generate_melspecs",
+__all__ = ["combine_audio", "HifiGan", "iSTFT", "inverse_stft", "ResBlock1", "ResBlock2", "get_padding", "init_weights", "TorchSTFT", "generate_melspecs",
            "dynamic_range_compression", "dynamic_range_decompression"]

@@ -25,6 +25,7 @@ class VocConfig(ctypes.Structure):
         ("resblock_kernel_sizes", c_int32 * E2E_MAX_KERNELS),
         ("num_dilations", c_int32 * E2E_MAX_KERNELS),
         ("resblock_dilation_sizes", (c_int32 * E2E_MAX_DILATIONS) * E2E_MAX_KERNELS),
+        ("istft_n_fft", c_int32),
     ]
 
 
@@ -39,6 +40,10 @@ SYMBOLS = {
                                 c_void_p, c_size_t, c_void_p]),
     "e2e_voc_forward_pcm16": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p,
                                       c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "e2e_voc_forward_spec": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p,
+                                     c_void_p, c_void_p, c_size_t, c_void_p]),
+    "e2e_istft_forward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                  c_void_p]),
     "e2e_voc_set_profile_events": (c_int, [c_void_p, c_void_p, c_void_p]),
     "e2e_voc_hop": (c_int, [c_void_p]),
     "e2e_voc_launches_per_forward": (c_int, [c_void_p]),

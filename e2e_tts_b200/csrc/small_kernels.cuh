@@ -160,4 +160,105 @@ post_conv_tanh_generic_kernel(const __nv_bfloat16* __restrict__ act, const float
   }
 }
 
+// ---- iSTFTNet head (class iSTFT, generator.py:91-109) ----
+// ReflectionPad1d((1, 0)) on channels-last rows: out[b][0] = in[b][1], out[b][p] = in[b][p-1]; 16 bytes per thread.
+__global__ void __launch_bounds__(256)
+reflect_pad_left_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int B, int T, int C) {
+  const int per_row = C / 8;
+  const long long total = (long long)B * (T + 1) * per_row;
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int q = (int)(idx % per_row);
+  const long long row = idx / per_row;
+  const int p = (int)(row % (T + 1));
+  const int b = (int)(row / (T + 1));
+  const int src = p == 0 ? (T > 1 ? 1 : 0) : p - 1;
+  const uint4* s4 = reinterpret_cast<const uint4*>(in + ((long long)b * T + src) * C) + q;
+  reinterpret_cast<uint4*>(out + ((long long)b * (T + 1) + p) * C)[q] = __ldg(s4);
+}
+
+// y: conv_post output [B][F][ldy] fp32 (channels-last, ldy >= 2*nb).  spec[b][c][f] = exp(y[.][c]),
+// phase[b][c][f] = sin(y[.][nb + c]) for c < nb (generator.py:105-106).  A block transposes 32 frames through
+// shared memory so both the reads (along channels) and the writes (along frames) are coalesced.
+__global__ void __launch_bounds__(256)
+spec_phase_kernel(const float* __restrict__ y, int B, int F, int ldy, int nb, float* __restrict__ spec,
+                  float* __restrict__ phase) {
+  __shared__ float tile[32][65];
+  const int f0 = blockIdx.x * 32;
+  const int b = blockIdx.y;
+  const int nc = 2 * nb;  // <= 64
+  for (int i = threadIdx.x; i < 32 * nc; i += blockDim.x) {
+    const int f = i / nc, c = i - f * nc;
+    if (f0 + f < F) tile[f][c] = y[((long long)b * F + f0 + f) * ldy + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * nc; i += blockDim.x) {
+    const int c = i / 32, f = i - c * 32;
+    if (f0 + f >= F) continue;
+    const float v = tile[f][c];
+    if (c < nb) spec[((long long)b * nb + c) * F + f0 + f] = expf(v);
+    else phase[((long long)b * nb + (c - nb)) * F + f0 + f] = sinf(v);
+  }
+}
+
+// inverse_stft (stft.py:138-148) = torch.istft(mag * exp(i phase), n_fft, hop, win = n_fft, periodic Hann,
+// center=True): y[n] = sum_f w[i] x_f[i] / sum_f w[i]^2 with i = n + n_fft/2 - hop f and x_f = irfft of frame f,
+//   x_f[i] = (1/N) (Re X_0 + (-1)^i Re X_{N/2} + 2 sum_{0<k<N/2} (Re X_k cos(2 pi k i / N) - Im X_k sin(2 pi k i / N))).
+// A block produces 256 consecutive samples: the frames it touches are converted to (Re, Im) once in shared memory.
+constexpr int kIstftMaxN = 64;
+__global__ void __launch_bounds__(256)
+istft_small_kernel(const float* __restrict__ mag, const float* __restrict__ phase, int B, int F, int N, int hop,
+                   float* __restrict__ wav) {
+  extern __shared__ float sm[];
+  const int nb = N / 2 + 1;
+  const int L = hop * (F - 1);
+  const int n0 = blockIdx.x * 256;
+  const int b = blockIdx.y;
+  float* cs = sm;            // [N] cos(2 pi j / N)
+  float* sn = cs + N;        // [N] sin(2 pi j / N)
+  float* win = sn + N;       // [N] periodic Hann
+  float* xr = win + N;       // [nfr][nb]
+  const int g0 = n0 + N / 2;                       // untrimmed index of the block's first sample
+  const int f_lo = max(0, (g0 - (N - 1) + hop - 1) / hop);
+  const int f_hi = min(F - 1, (g0 + 255) / hop);
+  const int nfr = f_hi - f_lo + 1;
+  float* xi = xr + (256 / hop + N / hop + 2) * nb;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    float s, c;
+    sincospif(2.0f * (float)j / (float)N, &s, &c);
+    cs[j] = c;
+    sn[j] = s;
+    win[j] = 0.5f - 0.5f * c;
+  }
+  for (int i = threadIdx.x; i < nfr * nb; i += blockDim.x) {
+    const int fr = i / nb, k = i - fr * nb;
+    const long long src = ((long long)b * nb + k) * F + f_lo + fr;
+    float s, c;
+    sincosf(phase[src], &s, &c);
+    const float m = mag[src];
+    xr[fr * nb + k] = m * c;
+    xi[fr * nb + k] = m * s;
+  }
+  __syncthreads();
+  const int n = n0 + threadIdx.x;
+  if (n >= L) return;
+  const int g = n + N / 2;
+  float num = 0.f, den = 0.f;
+  const int fa = max(f_lo, (g - (N - 1) + hop - 1) / hop), fb = min(f_hi, g / hop);
+  for (int f = fa; f <= fb; ++f) {
+    const int i = g - hop * f;  // 0 <= i < N
+    const float* re = xr + (f - f_lo) * nb;
+    const float* im = xi + (f - f_lo) * nb;
+    float acc = re[0] + ((i & 1) ? -re[nb - 1] : re[nb - 1]);
+    for (int k = 1; k < nb - 1; ++k) {
+      const int j = (k * i) & (N - 1);  // N is a power of two
+      acc += 2.0f * (re[k] * cs[j] - im[k] * sn[j]);
+    }
+    const float w = win[i];
+    num = fmaf(w, acc / (float)N, num);
+    den = fmaf(w, w, den);
+  }
+  wav[(long long)b * L + n] = num / den;
+}
+
 }  // namespace e2e

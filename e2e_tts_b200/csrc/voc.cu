@@ -14,7 +14,7 @@ using namespace e2e;
 
 namespace {
 
-enum LayerKind { L_CONV = 0, L_CONVT = 1, L_POST = 2 };
+enum LayerKind { L_CONV = 0, L_CONVT = 1, L_POST = 2 };  // (the iSTFTNet conv_post is an L_CONV padded to 32 columns)
 
 struct Layer {
   std::string name;
@@ -70,7 +70,9 @@ struct e2e_voc {
 
 static int pick_nt(int cout) { return cout >= 256 ? 256 : cout; }
 
-static void add_conv(e2e_voc* v, const std::string& name, int cin, int cin_pad, int cout, int k, int dil) {
+static void add_conv(e2e_voc* v, const std::string& name, int cin, int cin_pad, int cout, int k, int dil,
+                     int cout_pad = 0) {
+  if (cout_pad < cout) cout_pad = cout;  // GEMM columns (zero weights / bias beyond cout)
   Layer L;
   L.name = name;
   L.kind = L_CONV;
@@ -80,10 +82,10 @@ static void add_conv(e2e_voc* v, const std::string& name, int cin, int cin_pad, 
   L.dil = dil;
   L.u = 1;
   L.shape.cin = cin_pad;
-  L.shape.n_total = cout;
-  L.shape.nt = pick_nt(cout);
+  L.shape.n_total = cout_pad;
+  L.shape.nt = pick_nt(cout_pad);
   L.shape.taps = k;
-  const int n_tiles = cout / L.shape.nt;
+  const int n_tiles = cout_pad / L.shape.nt;
   for (int i = 0; i < n_tiles; ++i)
     for (int j = 0; j < k; ++j) L.shape.shifts.push_back((j - (k - 1) / 2) * dil);
   v->by_name[name] = (int)v->layers.size();
@@ -166,7 +168,13 @@ extern "C" int e2e_voc_create(const e2e_voc_config* cfg, e2e_voc** out) {
       }
     }
   }
-  {
+  if (cfg->istft_n_fft > 0) {
+    // iSTFTNet head: conv_post C -> n_fft + 2, k = 7 (generator.py:86) on the tensor cores, columns padded to 32
+    const int n = cfg->istft_n_fft;
+    if (n < 4 || n > 62 || (n & 1)) return fail(-4, "gen_istft_n_fft must be even, in [4, 62]");
+    if (ch != 32 && ch % 64 != 0) return fail(-4, "conv_post input channels unsupported");
+    add_conv(v.get(), "conv_post", ch, ch, n + 2, 7, 1, (n + 2 + 31) / 32 * 32);
+  } else {
     Layer L;
     L.name = "conv_post";
     L.kind = L_POST;
@@ -302,7 +310,8 @@ static void carve(const e2e_voc* v, int B, int T, void* ws, Buffers& b) {
     off += align_up(bytes, 1024);
     return r;
   };
-  const size_t E = stage_elems(v, B, T);
+  // + one row per utterance: the iSTFTNet head reflection-pads the last stage's tensor (generator.py:102)
+  const size_t E = stage_elems(v, B, T) + (size_t)B * v->cfg.upsample_initial_channel;
   b.melA = (__nv_bfloat16*)take((size_t)B * T * v->cin_pad * 2);
   b.preA = (__nv_bfloat16*)take((size_t)B * T * v->cfg.upsample_initial_channel * 2);
   b.A0 = (__nv_bfloat16*)take(E * 2);
@@ -476,6 +485,25 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
     }
     stage_in = bf.Y;
   }
+  if (c.istft_n_fft > 0) {
+    // iSTFTNet head (generator.py:101-106): ReflectionPad1d((1, 0)) -> conv_post on T_s + 1 rows -> exp / sin.
+    // A0 holds the padded tensor, A1 (reinterpreted) conv_post's fp32 output [B][T_s + 1][32k].
+    Op pad;
+    pad.kind = 5;
+    pad.layer = 0;
+    ops.push_back(pad);
+    const int lp = v->by_name["conv_post"];
+    if ((size_t)v->layers[lp].shape.n_total * 4 > (size_t)v->layers[lp].cin * 2)
+      return fail(-4, "iSTFTNet head: conv_post output does not fit the scratch tensor");
+    rc = make_conv_op(v, ops, lp, B, Ts + 1, bf.A0, nullptr, nullptr, reinterpret_cast<float*>(bf.A1), nullptr, 1.0f,
+                      0.f);
+    if (rc) return rc;
+    Op fin;
+    fin.kind = 6;
+    fin.layer = lp;
+    ops.push_back(fin);
+    return 0;
+  }
   {
     Op op;
     op.kind = 2;
@@ -497,9 +525,20 @@ extern "C" int e2e_voc_launches_per_forward(const e2e_voc* v) {
   return n;
 }
 
+struct SpecOut {
+  float* spec = nullptr;
+  float* phase = nullptr;
+};
+
 static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B, int32_t T,
-                            const PostOut& post, void* workspace, size_t workspace_bytes, void* stream) {
-  if (!v || !mel || (!post.wav && !post.pcm) || !workspace) return fail(-1, "null argument");
+                            const PostOut& post, const SpecOut& so, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  if (!v || !mel || !workspace) return fail(-1, "null argument");
+  if (v->cfg.istft_n_fft > 0) {
+    if (!so.spec || !so.phase) return fail(-1, "this generator has the iSTFTNet head: call e2e_voc_forward_spec");
+  } else if (!post.wav && !post.pcm) {
+    return fail(-1, "this generator has the HiFi-GAN head: call e2e_voc_forward / e2e_voc_forward_pcm16");
+  }
   if (B < 1 || T < 1) return fail(-1, "B and T must be positive");
   if (e2e_voc_missing_layers(v) != 0) return fail(-7, "e2e_voc_forward before all layers were loaded");
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(-1, "workspace must be 1024-byte aligned");
@@ -537,6 +576,16 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
     } else if (op.kind == 3) {
       int rc = launch_pair(op.pair, st);
       if (rc) return rc;
+    } else if (op.kind == 5) {
+      const int Ts = T * v->hop, C = v->layers[v->by_name["conv_post"]].cin;
+      const long long total = (long long)B * (Ts + 1) * (C / 8);
+      reflect_pad_left_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(bf.Y, bf.A0, B, Ts, C);
+    } else if (op.kind == 6) {
+      const Layer& L = v->layers[op.layer];
+      const int F = T * v->hop + 1, nb = v->cfg.istft_n_fft / 2 + 1;
+      dim3 grid((F + 31) / 32, B);
+      spec_phase_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(bf.A1), B, F, L.shape.n_total, nb,
+                                              so.spec, so.phase);
     } else {
       const Layer& L = v->layers[op.layer];
       const int Tout = T * v->hop;
@@ -563,7 +612,7 @@ extern "C" int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t
                                int32_t T, float* wav, void* workspace, size_t workspace_bytes, void* stream) {
   if (!wav) return fail(-1, "null argument");
   PostOut post{wav, nullptr, nullptr, v ? v->hop : 1, 1.0f};
-  return voc_forward_impl(v, mel, sB, sC, sT, B, T, post, workspace, workspace_bytes, stream);
+  return voc_forward_impl(v, mel, sB, sC, sT, B, T, post, SpecOut{}, workspace, workspace_bytes, stream);
 }
 
 extern "C" int e2e_voc_forward_pcm16(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B,
@@ -572,7 +621,36 @@ extern "C" int e2e_voc_forward_pcm16(e2e_voc* v, const float* mel, int64_t sB, i
   if (!pcm) return fail(-1, "null argument");
   if (!(max_wav_value > 0.f) || max_wav_value > 32768.f) return fail(-1, "max_wav_value must be in (0, 32768]");
   PostOut post{nullptr, pcm, mel_lengths, v ? v->hop : 1, max_wav_value};
-  return voc_forward_impl(v, mel, sB, sC, sT, B, T, post, workspace, workspace_bytes, stream);
+  return voc_forward_impl(v, mel, sB, sC, sT, B, T, post, SpecOut{}, workspace, workspace_bytes, stream);
+}
+
+extern "C" int e2e_voc_forward_spec(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B,
+                                    int32_t T, float* spec, float* phase, void* workspace, size_t workspace_bytes,
+                                    void* stream) {
+  if (!spec || !phase) return fail(-1, "null argument");
+  if (v && v->cfg.istft_n_fft <= 0) return fail(-1, "e2e_voc_forward_spec needs a generator created with istft_n_fft > 0");
+  SpecOut so;
+  so.spec = spec;
+  so.phase = phase;
+  PostOut post{nullptr, nullptr, nullptr, v ? v->hop : 1, 1.0f};
+  return voc_forward_impl(v, mel, sB, sC, sT, B, T, post, so, workspace, workspace_bytes, stream);
+}
+
+extern "C" int e2e_istft_forward(const float* mag, const float* phase, int32_t B, int32_t frames, int32_t n_fft,
+                                 int32_t hop, int32_t win, float* wav, void* stream) {
+  if (!mag || !phase || !wav) return fail(-1, "null argument");
+  if (B < 1 || B > 65535 || frames < 2) return fail(-1, "need B in [1, 65535] and at least two frames");
+  if (n_fft < 4 || n_fft > kIstftMaxN || (n_fft & (n_fft - 1)) || win != n_fft || hop < 1 || n_fft % hop)
+    return fail(-4, "inverse STFT supported for win == n_fft = 2^m <= 64 and hop dividing n_fft");
+  const int nb = n_fft / 2 + 1;
+  const int L = hop * (frames - 1);
+  const size_t smem = (size_t)(3 * n_fft + 2 * (256 / hop + n_fft / hop + 2) * nb) * 4;
+  if (smem > 48 * 1024) return fail(-4, "inverse STFT: hop too small for the shared-memory budget");
+  dim3 grid((L + 255) / 256, B);
+  istft_small_kernel<<<grid, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(mag, phase, B, frames, n_fft, hop, wav);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, std::string("istft launch: ") + cudaGetErrorString(e));
+  return 0;
 }
 
 extern "C" const char* e2e_last_error_string(void) { return last_error().c_str(); }

@@ -189,3 +189,28 @@ def generate_melspecs(y, n_fft=1024, num_mels=80, sampling_rate=22050, hop_size=
     if int(flag.item()) != 0:
         warnings.warn("input has samples outside [-1, 1] (min %g, max %g)" % (float(x.min()), float(x.max())))
     return mel.cpu() if was_cpu else mel
+
+
+def inverse_stft(magnitude: torch.Tensor, phase: torch.Tensor, n_fft: int = 1024, hop_size: int = 256,
+                 win_size: int = 1024) -> torch.Tensor:
+    """stft.py:138-148: torch.istft(magnitude * exp(i * phase), n_fft, hop_size, win_size, hann_window(win_size))
+    .unsqueeze(-2).  magnitude, phase: [B, n_fft/2 + 1, frames] fp32 CUDA tensors -> [B, 1, hop_size * (frames - 1)].
+    Runs the small-transform CUDA kernel (win_size == n_fft = 2^m <= 64, the iSTFTNet head's 16 / 4 / 16); other sizes
+    are outside the synthesis path and raise (no CPU fallback)."""
+    if magnitude.shape != phase.shape or magnitude.dim() != 3 or magnitude.shape[1] != n_fft // 2 + 1:
+        raise ValueError("expected magnitude and phase of shape [B, %d, frames]" % (n_fft // 2 + 1))
+    if not magnitude.is_cuda or not phase.is_cuda:
+        raise RuntimeError("e2e_tts_b200.inverse_stft runs on CUDA (sm_100a) only; there is no CPU path")
+    mag = magnitude.detach().float().contiguous()
+    ph = phase.detach().float().contiguous()
+    B, _, frames = mag.shape
+    if B == 0:
+        return mag.new_zeros((0, 1, hop_size * max(frames - 1, 0)))
+    out = torch.empty((B, 1, hop_size * (frames - 1)), dtype=torch.float32, device=mag.device)
+    with torch.cuda.device(mag.device):
+        stream = torch.cuda.current_stream(mag.device).cuda_stream
+        rc = _native.lib().e2e_istft_forward(mag.data_ptr(), ph.data_ptr(), B, frames, int(n_fft), int(hop_size),
+                                             int(win_size), out.data_ptr(), stream)
+        _native.check(rc, "e2e_istft_forward")
+    return out
+

@@ -117,7 +117,7 @@ class HifiGan(nn.Module):
         c0 = int(config["upsample_initial_channel"])
         self.in_channels = 80  # hard-coded at generator.py:18
         self.conv_pre = _WNConv(self.in_channels, c0, 7)
-        self._resblock_type = 1 if config["resblock"] == 1 else 2  # generator.py:19
+        self._resblock_type = self._select_resblock(config)
         resblock = ResBlock1 if self._resblock_type == 1 else ResBlock2
         self.ups = nn.ModuleList()
         for i, (u, k) in enumerate(zip(config["upsample_rates"], config["upsample_kernel_sizes"])):
@@ -128,7 +128,8 @@ class HifiGan(nn.Module):
             ch = c0 // (2 ** (i + 1))
             for k, d in zip(config["resblock_kernel_sizes"], config["resblock_dilation_sizes"]):
                 self.resblocks.append(resblock(ch, int(k), tuple(int(x) for x in d)))
-        self.conv_post = _WNConv(ch, 1, 7)
+        self.post_n_fft = self._post_n_fft(config)   # 0: HiFi-GAN head; n: iSTFTNet head (conv_post -> n + 2)
+        self.conv_post = _WNConv(ch, self.post_n_fft + 2 if self.post_n_fft else 1, 7)
         self.hop = 1
         for u in config["upsample_rates"]:
             self.hop *= int(u)
@@ -137,6 +138,14 @@ class HifiGan(nn.Module):
         self._loaded_version = None  # parameter-version fingerprint the packed weights correspond to
         self._workspaces: Dict[tuple, torch.Tensor] = {}
         self._profile_events = None  # (cudaEvent_t, cudaEvent_t) handles for the next forward (measurement hook)
+
+    @staticmethod
+    def _select_resblock(config: dict) -> int:
+        return 1 if config["resblock"] == 1 else 2  # generator.py:19 (int compare)
+
+    @staticmethod
+    def _post_n_fft(config: dict) -> int:
+        return 0
 
     # ------------------------------------------------------------------ state-dict compatibility
     def _wn_layers(self) -> List[tuple]:
@@ -199,6 +208,7 @@ class HifiGan(nn.Module):
             cfg.upsample_rates[i] = int(u)
             cfg.upsample_kernel_sizes[i] = int(k)
         cfg.num_kernels = self.num_kernels
+        cfg.istft_n_fft = self.post_n_fft
         for j, (k, d) in enumerate(zip(c["resblock_kernel_sizes"], c["resblock_dilation_sizes"])):
             d = list(d)
             if self._resblock_type != 1:
@@ -330,3 +340,48 @@ class HifiGan(nn.Module):
                 self._handle = None
         except Exception:
             pass
+
+
+class iSTFT(HifiGan):
+    """iSTFTNet generator (reference class iSTFT, generator.py:65-119; `istft:` mapping of model_config.yaml:83-92;
+    selected by load_vocoder(use_complex=True), src/tools/tools_for_model.py:45-50).  Same trunk kernels as HifiGan
+    with the configured stages, then ReflectionPad1d((1, 0)), conv_post C -> gen_istft_n_fft + 2, exp / sin:
+
+        spec, phase = g(mel)                       # each [B, n_fft/2 + 1, hop*T + 1] fp32
+        wav = inverse_stft(spec, phase, n_fft, hop_size, win_size)   # e2e_tts_b200.inverse_stft, stft.py:138-148
+
+    The reference selects its residual block with `config['resblock'] == '1'` (a STRING compare, generator.py:71), so
+    the shipped config (`resblock: 1`, an int) builds ResBlock2; reproduced here so checkpoints load."""
+
+    @staticmethod
+    def _select_resblock(config: dict) -> int:
+        return 1 if config["resblock"] == "1" else 2  # generator.py:71
+
+    @staticmethod
+    def _post_n_fft(config: dict) -> int:
+        return int(config["gen_istft_n_fft"])  # generator.py:85
+
+    def forward(self, x: torch.Tensor):
+        """generator.py:91-109."""
+        self._check_input(x)
+        B, _, T = x.shape
+        nb = self.post_n_fft // 2 + 1
+        if B == 0 or T == 0:
+            z = x.new_zeros((B, nb, self.hop * T + (1 if T else 0)))
+            return z, z.clone()
+        with torch.cuda.device(x.device):
+            self._sync_native(x.device)
+            ws = self._workspace(B, T, x.device)
+            ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+            spec = torch.empty((B, nb, self.hop * T + 1), dtype=torch.float32, device=x.device)
+            phase = torch.empty_like(spec)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            rc = _native.lib().e2e_voc_forward_spec(self._handle, x.data_ptr(), x.stride(0), x.stride(1), x.stride(2),
+                                                    B, T, spec.data_ptr(), phase.data_ptr(), ws_ptr,
+                                                    ws.numel() - (ws_ptr - ws.data_ptr()), stream)
+            _native.check(rc, "e2e_voc_forward_spec")
+        return spec, phase
+
+    def forward_pcm16(self, *a, **kw):
+        raise RuntimeError("iSTFT returns (spec, phase); synthesise with inverse_stft(spec, phase, ...)")
+

@@ -40,6 +40,10 @@ typedef struct e2e_voc_config {
   int32_t resblock_kernel_sizes[E2E_MAX_KERNELS];
   int32_t num_dilations[E2E_MAX_KERNELS];
   int32_t resblock_dilation_sizes[E2E_MAX_KERNELS][E2E_MAX_DILATIONS];
+  /* 0: HiFi-GAN head, conv_post C->1 + tanh (generator.py:33,49-51).  n > 0: iSTFTNet head (class iSTFT,
+   * generator.py:65-109; `istft:` mapping, model_config.yaml:83-92) with gen_istft_n_fft = n: ReflectionPad1d((1,0)),
+   * conv_post C -> n+2, exp on the first n/2+1 channels, sin on the rest; use e2e_voc_forward_spec. */
+  int32_t istft_n_fft;
 } e2e_voc_config;
 
 typedef struct e2e_voc e2e_voc; /* opaque: packed bf16 weights + launch plans of one generator */
@@ -77,6 +81,17 @@ int e2e_voc_forward(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_
 int e2e_voc_forward_pcm16(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B, int32_t T,
                           const int32_t* mel_lengths, float max_wav_value, int16_t* pcm, void* workspace,
                           size_t workspace_bytes, void* stream);
+
+/* Replaces iSTFT.forward (generator.py:91-109) for a generator created with istft_n_fft = n > 0.  spec, phase:
+ * device fp32 [B][n/2+1][upsample*T + 1] (the reference's return layout; the +1 frame is the reflection pad). */
+int e2e_voc_forward_spec(e2e_voc* v, const float* mel, int64_t sB, int64_t sC, int64_t sT, int32_t B, int32_t T,
+                         float* spec, float* phase, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces inverse_stft (e2e_tts/src/tools/stft.py:138-148): torch.istft(mag * exp(i*phase), n_fft, hop, win,
+ * periodic Hann window, center=True) for the small transforms of the iSTFTNet head.  mag, phase: device fp32
+ * [B][n_fft/2+1][frames]; wav: device fp32 [B][hop*(frames-1)].  Supported: win == n_fft <= 64, n_fft % hop == 0. */
+int e2e_istft_forward(const float* mag, const float* phase, int32_t B, int32_t frames, int32_t n_fft, int32_t hop,
+                      int32_t win, float* wav, void* stream);
 
 /* Measurement hook: the NEXT e2e_voc_forward records `ev_begin` (a cudaEvent_t) on its stream just before its first
  * tensor-core convolution launch and `ev_end` right after its last one, then forgets both (one-shot).  bench.py

@@ -38,6 +38,27 @@ DEFAULT_CONFIG = {  # e2e_tts/config/model_config.yaml:75-82
 }
 
 
+ISTFT_CONFIG = {  # e2e_tts/config/model_config.yaml:83-92 (`istft:` mapping, class iSTFT)
+    "resblock": 1,
+    "gen_istft_n_fft": 16,
+    "gen_istft_hop_size": 4,
+    "gen_istft_win_size": 16,
+    "upsample_rates": [8, 8],
+    "upsample_kernel_sizes": [16, 16],
+    "upsample_initial_channel": 512,
+    "resblock_kernel_sizes": [3, 7, 11],
+    "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
+}
+
+
+def resblock_type(config: dict) -> int:
+    """HifiGan compares `config['resblock'] == 1` (generator.py:19); iSTFT compares with the STRING '1'
+    (generator.py:71), so the shipped `resblock: 1` selects ResBlock2 there."""
+    if "gen_istft_n_fft" in config:
+        return 1 if config["resblock"] == "1" else 2
+    return 1 if config["resblock"] == 1 else 2
+
+
 def get_padding(kernel_size: int, dilation: int = 1) -> int:
     return int((kernel_size * dilation - dilation) / 2)  # function.py:16-17
 
@@ -59,7 +80,7 @@ def layer_names(config: dict) -> List[tuple]:
     for i in range(len(config["upsample_rates"])):
         ch = c0 // 2 ** (i + 1)
         for k, d in zip(config["resblock_kernel_sizes"], config["resblock_dilation_sizes"]):
-            if config["resblock"] == 1:
+            if resblock_type(config) == 1:
                 for m in range(3):
                     out.append(("resblocks.%d.convs1.%d" % (n, m), "conv", ch, ch, k))
                 for m in range(3):
@@ -68,7 +89,8 @@ def layer_names(config: dict) -> List[tuple]:
                 for m in range(2):
                     out.append(("resblocks.%d.convs.%d" % (n, m), "conv", ch, ch, k))
             n += 1
-    out.append(("conv_post", "conv", ch, 1, 7))
+    n_post = config["gen_istft_n_fft"] + 2 if "gen_istft_n_fft" in config else 1   # generator.py:86 / :33
+    out.append(("conv_post", "conv", ch, n_post, 7))
     return out
 
 
@@ -116,6 +138,49 @@ def _weight(sd: dict, name: str, dtype) -> torch.Tensor:
 def hifigan_forward(sd: dict, config: dict, mel: torch.Tensor, dtype=torch.float32,
                     taps: Optional[dict] = None) -> torch.Tensor:
     """mel [B, 80, T] -> wav [B, 1, prod(upsample_rates)*T].  `taps`, if given, receives named intermediates."""
+    x = _trunk(sd, config, mel, dtype, taps)
+    x = F.leaky_relu(x)                                                                 # :49 (slope 0.01)
+    x = F.conv1d(x, _weight(sd, "conv_post", dtype), sd["conv_post.bias"].to(dtype), padding=3)   # :50
+    return torch.tanh(x)                                                                # :51
+
+
+def istft_forward(sd: dict, config: dict, mel: torch.Tensor, dtype=torch.float32):
+    """class iSTFT, generator.py:91-109: mel [B, 80, T] -> (spec, phase), each [B, n_fft/2+1, prod(rates)*T + 1]."""
+    n_fft = config["gen_istft_n_fft"]
+    x = _trunk(sd, config, mel, dtype, None)                                            # :92-101 (same as HifiGan)
+    x = F.leaky_relu(x)                                                                 # :102 (slope 0.01)
+    x = F.pad(x, (1, 0), mode="reflect")                                                # :103 ReflectionPad1d((1, 0))
+    x = F.conv1d(x, _weight(sd, "conv_post", dtype), sd["conv_post.bias"].to(dtype), padding=3)   # :104
+    spec = torch.exp(x[:, :n_fft // 2 + 1, :])                                          # :105
+    phase = torch.sin(x[:, n_fft // 2 + 1:, :])                                         # :106
+    return spec, phase
+
+
+def inverse_stft(magnitude: torch.Tensor, phase: torch.Tensor, n_fft=1024, hop_size=256, win_size=1024) -> torch.Tensor:
+    """e2e_tts/src/tools/stft.py:138-148, line for line."""
+    hann_window = torch.hann_window(win_size).to(magnitude.device)
+    inverse_transform = torch.istft(magnitude * torch.exp(phase * 1j), n_fft=n_fft, hop_length=hop_size,
+                                    win_length=win_size, window=hann_window)
+    return inverse_transform.unsqueeze(-2)
+
+
+def inverse_stft_def(mag: np.ndarray, phase: np.ndarray, n_fft: int, hop: int) -> np.ndarray:
+    """Definition of the same transform in float64 numpy (win == n_fft, periodic Hann, center=True):
+    overlap-add of w * irfft(frame) divided by the overlap-added w^2, n_fft/2 samples trimmed at both ends."""
+    B, nb, F_ = mag.shape
+    w = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n_fft) / n_fft)
+    X = mag.astype(np.float64) * np.exp(1j * phase.astype(np.float64))
+    total = n_fft + hop * (F_ - 1)
+    num, den = np.zeros((B, total)), np.zeros(total)
+    for f in range(F_):
+        num[:, hop * f: hop * f + n_fft] += np.fft.irfft(X[:, :, f], n=n_fft, axis=1) * w
+        den[hop * f: hop * f + n_fft] += w * w
+    lo, hi = n_fft // 2, total - n_fft // 2            # the trimmed edges are where the envelope vanishes
+    return num[:, lo:hi] / den[lo:hi]
+
+
+def _trunk(sd: dict, config: dict, mel: torch.Tensor, dtype, taps: Optional[dict]) -> torch.Tensor:
+    """conv_pre and the upsampling stages (generator.py:38-48; identical in iSTFT.forward, :92-101)."""
     x = mel.to(dtype)
     b = lambda n: sd[n + ".bias"].to(dtype)
     nk = len(config["resblock_kernel_sizes"])
@@ -134,7 +199,7 @@ def hifigan_forward(sd: dict, config: dict, mel: torch.Tensor, dtype=torch.float
             ks = config["resblock_kernel_sizes"][j]
             dil = config["resblock_dilation_sizes"][j]
             y = x
-            if config["resblock"] == 1:                                                 # layers.py:33-40
+            if resblock_type(config) == 1:                                              # layers.py:33-40
                 for m in range(3):
                     p1, p2 = "resblocks.%d.convs1.%d" % (n, m), "resblocks.%d.convs2.%d" % (n, m)
                     xt = F.leaky_relu(y, LRELU_SLOPE)
@@ -152,9 +217,7 @@ def hifigan_forward(sd: dict, config: dict, mel: torch.Tensor, dtype=torch.float
         x = xs / nk                                                                     # :48
         if taps is not None:
             taps["stage.%d" % i] = x
-    x = F.leaky_relu(x)                                                                 # :49 (slope 0.01)
-    x = F.conv1d(x, _weight(sd, "conv_post", dtype), b("conv_post"), padding=3)         # :50
-    return torch.tanh(x)                                                                # :51
+    return x
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -107,7 +107,33 @@ def main() -> None:
         np.savez_compressed(os.path.join(OUT, name + ".npz"), mel=mel.numpy(), wav=want.numpy(), seed=seed,
                             regime=regime, resblock=cfg["resblock"])
 
+    # iSTFTNet head: the reference's class iSTFT (generator.py:65-119) and inverse_stft (stft.py:138-148)
+    from vocoder.generator import iSTFT  # noqa  (same sys.path entry as HifiGan)
+    cfg = ho.ISTFT_CONFIG
+    sd = ho.make_state_dict(cfg, 31, "strong")
+    ref = iSTFT(cfg)
+    ref.load_state_dict(sd)
+    ref.eval()
+    mel = mel_like(2, 6, 131)
+    with torch.no_grad():
+        spec, phase = ref(mel)
+        ospec, ophase = ho.istft_forward(sd, cfg, mel)
+    e1 = ((ospec.log() - spec.log()).abs().max().item(), (ophase - phase).abs().max().item())
+    print("istft_strong: frames=%d oracle-vs-reference log-spec err=%.3g phase err=%.3g" % (spec.shape[-1], e1[0], e1[1]))
+    assert max(e1) < 1e-4
+
     TorchSTFT, generate_melspecs = _import_reference_stft()
+    from tools.stft import inverse_stft  # noqa
+    with torch.no_grad():
+        wav = inverse_stft(spec, phase, 16, 4, 16)
+        owav = ho.inverse_stft(spec, phase, 16, 4, 16)
+    dwav = ho.inverse_stft_def(spec.numpy(), phase.numpy(), 16, 4)
+    print("inverse_stft: len=%d oracle-vs-reference err=%.3g, float64 definition vs reference err=%.3g" %
+          (wav.shape[-1], (owav - wav).abs().max().item(), np.abs(dwav - wav[:, 0].numpy()).max()))
+    assert torch.equal(owav, wav) and np.abs(dwav - wav[:, 0].numpy()).max() < 1e-5 * float(wav.abs().max())
+    np.savez_compressed(os.path.join(OUT, "istft_strong.npz"), mel=mel.numpy(), spec=spec.numpy(), phase=phase.numpy(),
+                        wav=wav.numpy(), seed=31)
+
     stft = TorchSTFT()  # defaults == preprocessing_config.yaml:5-14
     import torchaudio
     fb = torchaudio.functional.melscale_fbanks(513, 0.0, 8000.0, 80, 22050, norm="slaney", mel_scale="slaney").T

@@ -102,3 +102,19 @@ def test_stft_public_attributes_and_helpers():
     assert torch.allclose(pkg.dynamic_range_decompression(pkg.dynamic_range_compression(x[1:])), x[1:])
     with pytest.raises(NotImplementedError):
         s.mel_spectrogram(torch.zeros(1, 4096), center=True)
+
+
+def test_istft_generator_contract():
+    """class iSTFT (generator.py:65-119): state-dict names, ResBlock selection quirk, head shape, no CPU path."""
+    from oracle import hifigan_oracle as ho
+    g = pkg.iSTFT(ho.ISTFT_CONFIG)
+    sd = ho.make_state_dict(ho.ISTFT_CONFIG, 1, "strong")
+    assert set(g.state_dict().keys()) == set(sd.keys())
+    g.load_state_dict(sd)
+    assert type(g.resblocks[0]).__name__ == "ResBlock2" and len(g.resblocks[0].convs) == 2
+    assert g.conv_post.weight_v.shape == (18, 128, 7) and g.hop == 64
+    assert type(pkg.iSTFT(dict(ho.ISTFT_CONFIG, resblock="1")).resblocks[0]).__name__ == "ResBlock1"
+    with pytest.raises(RuntimeError):
+        g(torch.zeros(1, 80, 4))
+    with pytest.raises(RuntimeError):
+        pkg.inverse_stft(torch.zeros(1, 9, 5), torch.zeros(1, 9, 5), 16, 4, 16)

@@ -119,3 +119,26 @@ def test_mel_range_assert_and_silence_floor():
     mel, energy = mo.mel_spectrogram(torch.zeros(1, 2048), return_energy=True)
     assert torch.allclose(mel, torch.full_like(mel, float(np.log(1e-5))))          # clamp floor, -11.51
     assert torch.allclose(energy, torch.full_like(energy, float(np.sqrt(513e-9))), rtol=1e-5)
+
+
+# ---- iSTFTNet head (SURVEY.md §8 f, N1): class iSTFT (generator.py:65-119) + inverse_stft (stft.py:138-148) ----
+def test_istft_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, "istft_strong.npz"))
+    sd = ho.make_state_dict(ho.ISTFT_CONFIG, int(g["seed"]), "strong")
+    with torch.no_grad():
+        spec, phase = ho.istft_forward(sd, ho.ISTFT_CONFIG, torch.from_numpy(g["mel"]))
+        wav = ho.inverse_stft(torch.from_numpy(g["spec"]), torch.from_numpy(g["phase"]), 16, 4, 16)
+    assert spec.shape == g["spec"].shape == (2, 9, 64 * 6 + 1)
+    assert (spec.log() - torch.from_numpy(g["spec"]).log()).abs().max().item() < 1e-4
+    assert (phase - torch.from_numpy(g["phase"])).abs().max().item() < 1e-4
+    assert torch.equal(wav, torch.from_numpy(g["wav"])) and wav.shape == (2, 1, 256 * 6)
+    d = ho.inverse_stft_def(g["spec"], g["phase"], 16, 4)
+    assert np.abs(d - g["wav"][:, 0]).max() < 1e-5 * np.abs(g["wav"]).max()
+
+
+def test_istft_selects_resblock2_for_the_shipped_int_config():
+    """generator.py:71 compares config['resblock'] with the string '1'."""
+    names = [n for n, *_ in ho.layer_names(ho.ISTFT_CONFIG)]
+    assert "resblocks.0.convs.1" in names and "resblocks.0.convs1.0" not in names and len(names) == 16
+    cfg = dict(ho.ISTFT_CONFIG, resblock="1")
+    assert "resblocks.0.convs1.2" in [n for n, *_ in ho.layer_names(cfg)]
