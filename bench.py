@@ -48,6 +48,17 @@ def peaks():
         return 1400.0, "fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained)"
 
 
+def ncu_traffic():
+    """DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the tcgen05 launches of ONE step, from the committed
+    ncu capture of this same command (scripts/gpu_final_profile.sh -> profiles/roofline_traffic.json); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_step_tcgen05"]), str(t.get("source", ""))
+    except Exception:
+        return None, ""
+
+
 def mel_like(B, T, seed):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(B, 80, T, generator=g) * 2.0 - 5.0).clamp(-11.5, 2.0)
@@ -257,6 +268,7 @@ def main():
     e2e_value = audio_s_step / (t.item() / args.steps * 1e-3)
 
     peak, peak_src = peaks()
+    traffic, traffic_src = ncu_traffic()
     conv_tflops = B * T * CONV_TC_FLOP_PER_FRAME / (conv_ms * 1e-3) * 1e-12
     launches = voc.launches_per_forward()
     line = {
@@ -272,8 +284,9 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 80 * T * 4, "d2h_bytes_per_step": B * S * 4},
         "gpu_launches": launches * args.steps,
         "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s",
-                     "frac": conv_tflops / peak, "traffic": None, "kernel": "pair_tc_kernel+conv_tc_kernel",
+                     "frac": conv_tflops / peak, "traffic": traffic, "kernel": "pair_tc_kernel+conv_tc_kernel",
                      "peak_source": peak_src,
+                     "traffic_note": ("DRAM bytes per step over the same launches, " + traffic_src) if traffic else "",
                      "note": "%d tcgen05 launches per step (pair_tc_kernel + conv_tc_kernel: the same implicit-GEMM "
                              "pipeline, fused and unfused), %.3f ms of the %.3f ms step" %
                              (launches - 2, conv_ms, ms_step)},
