@@ -12,9 +12,10 @@
 // 512-k from one pair of loads (X[512-k] = conj(Ze - W^k Zo)) and only the bins the filterbank reads (0..371 for
 // fmax = 8 kHz).  The frame energy sqrt(sum_k mag_k^2) over all 513 bins comes from Parseval's identity on the
 // windowed samples: sum_{k<=512} |X_k|^2 = (1024 sum_n xw_n^2 + X_0^2 + X_512^2) / 2 (shuffle-reduced).  The mel
-// filterbank is applied in its sparse form (727 non-zeros instead of a dense 80x513 GEMM) with the non-zeros
-// split evenly over the 64 threads of a frame (fixed-order partial sums: deterministic); outputs are staged so
-// that the global stores of mel[b][m][t0..t0+32) are 128-byte coalesced.  The index maps are emulated and
+// filterbank is applied in its sparse, block form: thread t of a frame owns BPT consecutive bins and the (at most FPB)
+// triangular filters that overlap them, as a dense FPB x BPT block of weights - branch-free, conflict-free, and
+// deterministic (fixed-order partial sums per filter); outputs are staged so that the global stores of
+// mel[b][m][t0..t0+32) are 128-byte coalesced.  The index maps are emulated and
 // checked on the CPU in tests/test_mel_fft_plan.py.
 #include <cmath>
 #include <cstring>
@@ -36,24 +37,23 @@ constexpr int kGroups = 4;                // 64-thread FFT groups per CTA
 constexpr int kThreads = kGroups * 64;
 constexpr int kAudio = (kF - 1) * kHop + kNfft;  // samples staged per CTA
 constexpr int kSx = 576;                  // padded complex exchange buffer (8 rows of 72 / 64 rows of 9)
-constexpr int kMagPad = 528;
-constexpr int kFbPerMax = 17;             // filterbank non-zeros per thread (64 threads: up to 1088 non-zeros)
-constexpr int kFbSplit = 8;               // partial-sum slots per filter (a filter's non-zeros span <= 8 threads)
+constexpr int kMagPad = 584;              // 64 blocks x pitch 9 (BPT = 8), multiple of 4
+constexpr int kFbSplitMax = 12;           // partial-sum slots per filter (a filter spans <= 12 threads' bin blocks)
 
 struct MelParams {
   const float* wav;
   long long ldw, L;
   int B, T, n_mels, nnz;
   int nb;               // bins the filterbank reads: 1 + last non-zero column of the basis
-  int fb_per;           // filterbank non-zeros per thread (== the kernel's PER)
+  int fb_split;         // partial-sum slots per filter = the most bin blocks any filter overlaps
   float* mel;
   float* energy;
   int* range_flag;
   const float* window;  // [1024] periodic Hann
   const float2* tw;     // [1024] exp(-2 pi i j / 1024)
-  const float2* fb_ent; // [fb_per][64] (weight, bits of (bin | last << 10 | slot << 11)): entry i of thread t.
-                        // `last` = the thread's last non-zero of that filter: the running sum goes to part[slot]
-                        // (slot = mel * kFbSplit + index of the thread among the filter's threads); padding: 0
+  const float4* fb_w;   // [ceil(FPB*BPT/4)][64] weights of thread t's block: element j*BPT + i = basis[filter j][bin i]
+  const int* fb_slot;   // [FPB][64] where filter j of thread t leaves its partial sum: mel * fb_split + (index of the
+                        // thread among the filter's threads); unused j -> the scratch slot n_mels * fb_split
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT: max relative error 2^-23 (PTX ISA)
@@ -95,10 +95,10 @@ __device__ __forceinline__ void group_sync(int g) {
   asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");
 }
 
-// PER = filterbank non-zeros per thread (odd: the 64 threads of a frame then read `mag` with an odd stride, which
-// spreads them over the shared-memory banks); 13 covers the e2e-tts basis (727 non-zeros), 17 any basis the
-// constructor accepts.
-template <int PER>
+// BPT = bins per thread, FPB = filters per bin block.  <6, 5> covers the e2e-tts basis (372 bins, 80 Slaney filters),
+// <8, 8> any triangular bank on <= 512 bins the constructor accepts.  The magnitudes are stored with a row pitch of
+// BPT | 1 words per block, so the 64 threads read their blocks with an odd stride (no bank conflicts).
+template <int BPT, int FPB>
 __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* audio = reinterpret_cast<float*>(smem);                    // [kAudio]
@@ -108,8 +108,12 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
   float* out_s = mag_all + kGroups * kMagPad;                       // [n_mels][kF+1]
   float* energy_s = out_s + ((p.n_mels * (kF + 1) + 3) & ~3);       // [kF]
   float* red_s = energy_s + kF;                                     // [kGroups][2]
-  float* part_all = red_s + kGroups * 2;                            // [kGroups][n_mels][kFbSplit]
-  float2* fb_ent_s = reinterpret_cast<float2*>(part_all + kGroups * p.n_mels * kFbSplit);  // [fb_per][64]
+  constexpr int PITCH = BPT | 1;
+  constexpr int NW4 = (FPB * BPT + 3) / 4;
+  const int part_n = (p.n_mels + 1) * p.fb_split;                   // + the scratch slot row
+  float* part_all = red_s + kGroups * 2;                            // [kGroups][n_mels + 1][fb_split]
+  float4* fb_w_s = reinterpret_cast<float4*>(part_all + ((kGroups * part_n + 3) & ~3));  // [NW4][64]
+  int* fb_slot_s = reinterpret_cast<int*>(fb_w_s + NW4 * 64);       // [FPB][64]
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
@@ -153,8 +157,10 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
     }
     if (bad && p.range_flag) atomicOr(p.range_flag, 1);
     for (int i = tid; i < 512; i += kThreads) tw_s[i] = p.tw[i];
-    for (int i = tid; i < 64 * PER; i += kThreads) fb_ent_s[i] = p.fb_ent[i];
-    for (int i = tid; i < kGroups * p.n_mels * kFbSplit; i += kThreads) part_all[i] = 0.f;  // unused slots stay 0
+    for (int i = tid; i < NW4 * 64; i += kThreads) fb_w_s[i] = p.fb_w[i];
+    for (int i = tid; i < FPB * 64; i += kThreads) fb_slot_s[i] = p.fb_slot[i];
+    for (int i = tid; i < kGroups * part_n; i += kThreads) part_all[i] = 0.f;   // unused slots stay 0
+    for (int i = tid; i < kGroups * kMagPad; i += kThreads) mag_all[i] = 0.f;   // bins past nb: weight 0 x finite
   }
 
   const int g = tid >> 6;   // FFT group
@@ -163,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
   float2* S1 = sx + g * 2 * kSx;
   float2* S2 = S1 + kSx;
   float* mag = mag_all + g * kMagPad;
-  float* part = part_all + g * p.n_mels * kFbSplit;
+  float* part = part_all + g * part_n;
   const int nb = p.nb;
 
   // per-thread constants: window taps and twiddles of passes 1 and 2
@@ -229,8 +235,8 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
       const float2 x = cadd(ze, wz), xp = csub(ze, wz);
       const float s = x.x * x.x + x.y * x.y + 1e-9f;  // stft.py:77
       const float sp = xp.x * xp.x + xp.y * xp.y + 1e-9f;
-      if (k < nb) mag[k] = sqrt_approx(s);
-      if (512 - k < nb) mag[512 - k] = sqrt_approx(sp);
+      if (k < nb) mag[k + (k / BPT) * (PITCH - BPT)] = sqrt_approx(s);
+      if (512 - k < nb) mag[(512 - k) + ((512 - k) / BPT) * (PITCH - BPT)] = sqrt_approx(sp);
       if (k == 0) {
         x0sq = x.x * x.x;
         xnsq = xp.x * xp.x;
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
     }
     if (t == 0 && 256 < nb) {
       const float2 z = S1[256 + 32];
-      mag[256] = sqrt_approx(z.x * z.x + z.y * z.y + 1e-9f);
+      mag[256 + (256 / BPT) * (PITCH - BPT)] = sqrt_approx(z.x * z.x + z.y * z.y + 1e-9f);
     }
     // energy^2 = sum_{k=0..512} (|X_k|^2 + 1e-9) = (1024 sum xw^2 + X_0^2 + X_512^2) / 2 + 513e-9   (stft.py:84)
     e = fmaf(1024.f, e, x0sq + xnsq);
@@ -246,32 +252,35 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if ((t & 31) == 0) red_s[g * 2 + (t >> 5)] = e;
     group_sync(g);
-    // sparse mel filterbank (stft.py:80): thread t multiplies its fb_per consecutive non-zeros; whenever it finishes
-    // a filter, the running sum goes to that filter's slot of this thread (branch-free: predicated store + select)
+    // sparse mel filterbank (stft.py:80): thread t applies the FPB x BPT weight block of its bins and leaves one
+    // partial sum per filter in that filter's slot of this thread
     {
-      // all entry loads, then all magnitude loads, are issued before the (serial) multiply-add chain
-      float2 en[PER];
-      float mv[PER];
+      float mv[BPT];
 #pragma unroll
-      for (int i = 0; i < PER; ++i) en[i] = fb_ent_s[i * 64 + t];
+      for (int i = 0; i < BPT; ++i) mv[i] = mag[t * PITCH + i];
+      float w[NW4 * 4];
 #pragma unroll
-      for (int i = 0; i < PER; ++i) mv[i] = mag[__float_as_int(en[i].y) & 0x3ff];
-      float acc = 0.f;
+      for (int q = 0; q < NW4; ++q) {
+        const float4 v = fb_w_s[q * 64 + t];
+        w[4 * q] = v.x;
+        w[4 * q + 1] = v.y;
+        w[4 * q + 2] = v.z;
+        w[4 * q + 3] = v.w;
+      }
 #pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        const int code = __float_as_int(en[i].y);
-        acc = fmaf(en[i].x, mv[i], acc);
-        if (code & 0x400) part[code >> 11] = acc;
-        acc = (code & 0x400) ? 0.f : acc;
+      for (int j = 0; j < FPB; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) acc = fmaf(w[j * BPT + i], mv[i], acc);
+        part[fb_slot_s[j * 64 + t]] = acc;
       }
     }
     if (t == 0) energy_s[fl] = sqrtf(0.5f * (red_s[g * 2] + red_s[g * 2 + 1]) + 513e-9f);
     group_sync(g);
     // fixed-order sum of the partials + log compression (stft.py:81, utils.py:28)
     for (int m = t; m < p.n_mels; m += 64) {
-      const float4 q0 = *reinterpret_cast<const float4*>(part + m * kFbSplit);
-      const float4 q1 = *reinterpret_cast<const float4*>(part + m * kFbSplit + 4);
-      const float acc = ((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w));
+      float acc = 0.f;
+      for (int q = 0; q < p.fb_split; ++q) acc += part[m * p.fb_split + q];
       out_s[m * (kF + 1) + fl] = logf(fmaxf(acc, 1e-5f));
     }
   }
@@ -289,10 +298,11 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
 
 struct e2e_mel {
   int n_fft, hop, win, n_mels, nnz;
-  int nb = 0, fb_per = 1;
+  int nb = 0, split = 1, variant = 0;  // variant 0: mel_kernel<6, 5>, 1: mel_kernel<8, 8>
   float* d_window = nullptr;
   float2* d_tw = nullptr;
-  float2* d_ent = nullptr;
+  float4* d_fbw = nullptr;
+  int* d_slot = nullptr;
   int smem_bytes = 0;
 };
 
@@ -302,37 +312,60 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
   if (n_fft != kNfft || win_length != kNfft || hop_length != kHop)
     return fail(-4, "mel front-end supports n_fft == win_length == 1024 and hop_length == 256 (the e2e-tts config)");
   if (n_mels < 1 || n_mels > 128) return fail(-4, "n_mels must be in [1, 128]");
-  // sparse filterbank: the non-zeros in (filter, bin) order, cut into 64 equal runs (one per thread of a frame)
-  struct Ent { float w; int mel, bin; };
-  std::vector<Ent> ents;
-  int nb = 1;
+  // sparse filterbank in block form: thread t of a frame owns bins [t*BPT, (t+1)*BPT) and the filters overlapping them
+  int nb = 1, nnz = 0;
   for (int r = 0; r < n_mels; ++r)
-    for (int k = 0; k < kBins; ++k) {
-      const float w = mel_basis[(size_t)r * kBins + k];
-      if (w != 0.f) {
-        ents.push_back({w, r, k});
+    for (int k = 0; k < kBins; ++k)
+      if (mel_basis[(size_t)r * kBins + k] != 0.f) {
+        ++nnz;
         nb = k + 1 > nb ? k + 1 : nb;
       }
-    }
-  const int nnz = (int)ents.size();
-  if (nnz > 64 * kFbPerMax) return fail(-4, "mel filterbank too dense (more than 1088 non-zeros)");
-  const int per = nnz <= 64 * 13 ? 13 : kFbPerMax;  // the two instantiations of mel_kernel
-  // entry i of thread t = non-zero number t * per + i, stored [i][t] (conflict-free for the 64 threads)
-  std::vector<float2> packed((size_t)64 * per, make_float2(0.f, 0.f));
-  std::vector<int> first(n_mels, -1);
-  for (int idx = 0; idx < nnz; ++idx) {
-    const Ent& en = ents[idx];
-    const int t = idx / per, i = idx % per;
-    if (first[en.mel] < 0) first[en.mel] = t;
-    const int q = t - first[en.mel];
-    if (q >= kFbSplit) return fail(-4, "mel filterbank has a filter wider than the kernel's split (8 x per-thread run)");
-    // last non-zero of this filter held by thread t?
-    const bool last = idx + 1 == nnz || ents[idx + 1].mel != en.mel || (idx + 1) / per != t;
-    const int code = en.bin | (last ? 0x400 : 0) | ((en.mel * kFbSplit + q) << 11);
-    float cf;
-    memcpy(&cf, &code, 4);
-    packed[(size_t)i * 64 + t] = make_float2(en.w, cf);
+  if (nb > 512) return fail(-4, "mel filterbank reaches the Nyquist bin: unsupported (fmax must be below sr/2)");
+  int variant = -1, BPT = 0, FPB = 0, split = 1;
+  std::vector<float> wblk;
+  std::vector<int> slot;
+  for (int v = 0; v < 2 && variant < 0; ++v) {
+    BPT = v == 0 ? 6 : 8;
+    FPB = v == 0 ? 5 : 8;
+    if (64 * BPT < nb) continue;
+    const int nw4 = (FPB * BPT + 3) / 4;
+    // filters of every block, and the blocks of every filter
+    std::vector<std::vector<int>> filt(64);
+    std::vector<int> first(n_mels, -1), count(n_mels, 0);
+    bool fits = true;
+    for (int t = 0; t < 64 && fits; ++t)
+      for (int r = 0; r < n_mels; ++r) {
+        bool any = false;
+        for (int i = 0; i < BPT; ++i) {
+          const int k = t * BPT + i;
+          any = any || (k < kBins && mel_basis[(size_t)r * kBins + k] != 0.f);
+        }
+        if (!any) continue;
+        filt[t].push_back(r);
+        if (first[r] < 0) first[r] = t;
+        count[r] = t - first[r] + 1;  // blocks first..t (a gap inside a filter just leaves a zero partial)
+        if ((int)filt[t].size() > FPB) fits = false;
+      }
+    if (!fits) continue;
+    split = 1;
+    for (int r = 0; r < n_mels; ++r) split = count[r] > split ? count[r] : split;
+    if (split > kFbSplitMax) continue;
+    variant = v;
+    wblk.assign((size_t)nw4 * 4 * 64, 0.f);
+    slot.assign((size_t)FPB * 64, n_mels * split);  // unused filters of a block -> the scratch slot row
+    for (int t = 0; t < 64; ++t)
+      for (size_t j = 0; j < filt[t].size(); ++j) {
+        const int r = filt[t][j];
+        slot[j * 64 + t] = r * split + (t - first[r]);
+        for (int i = 0; i < BPT; ++i) {
+          const int k = t * BPT + i;
+          const int e = (int)j * BPT + i;  // element e of the thread's block lives in float4 e/4, lane e%4
+          wblk[((size_t)(e / 4) * 64 + t) * 4 + (e % 4)] = k < kBins ? mel_basis[(size_t)r * kBins + k] : 0.f;
+        }
+      }
   }
+  if (variant < 0)
+    return fail(-4, "mel filterbank does not fit the kernel's block form (<= 8 filters per 8-bin block, <= 12 blocks per filter)");
   e2e_mel* m = new e2e_mel;
   m->n_fft = n_fft;
   m->hop = hop_length;
@@ -340,7 +373,8 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
   m->n_mels = n_mels;
   m->nnz = nnz;
   m->nb = nb;
-  m->fb_per = per;
+  m->split = split;
+  m->variant = variant;
   std::vector<float> window(kNfft);
   std::vector<float2> tw(kNfft);
   const double pi = 3.14159265358979323846;
@@ -349,8 +383,12 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
     tw[n] = make_float2((float)cos(2.0 * pi * n / kNfft), (float)(-sin(2.0 * pi * n / kNfft)));
   }
   // mirrors the carve-up at the top of mel_kernel
-  m->smem_bytes = (kAudio + 2 * 512 + kGroups * 2 * kSx * 2 + kGroups * kMagPad + ((n_mels * (kF + 1) + 3) & ~3) + kF +
-                   kGroups * 2 + kGroups * n_mels * kFbSplit + 2 * 64 * per) * 4;
+  {
+    const int part_n = (n_mels + 1) * split;
+    const int nw4 = (FPB * BPT + 3) / 4;
+    m->smem_bytes = (kAudio + 2 * 512 + kGroups * 2 * kSx * 2 + kGroups * kMagPad + ((n_mels * (kF + 1) + 3) & ~3) + kF +
+                     kGroups * 2 + ((kGroups * part_n + 3) & ~3) + nw4 * 4 * 64 + FPB * 64) * 4;
+  }
   if (m->smem_bytes > 113 * 1024) {
     delete m;
     return fail(-4, "mel filterbank too dense for the shared-memory budget");
@@ -363,9 +401,10 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
   };
   up((void**)&m->d_window, window.data(), window.size() * 4);
   up((void**)&m->d_tw, tw.data(), tw.size() * 8);
-  up((void**)&m->d_ent, packed.data(), packed.size() * 8);
+  up((void**)&m->d_fbw, wblk.data(), wblk.size() * 4);
+  up((void**)&m->d_slot, slot.data(), slot.size() * 4);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(per == 13 ? mel_kernel<13> : mel_kernel<kFbPerMax>,
+    e = cudaFuncSetAttribute(variant == 0 ? mel_kernel<6, 5> : mel_kernel<8, 8>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
   if (e != cudaSuccess) {
     e2e_mel_destroy(m);
@@ -379,7 +418,8 @@ extern "C" void e2e_mel_destroy(e2e_mel* m) {
   if (!m) return;
   cudaFree(m->d_window);
   cudaFree(m->d_tw);
-  cudaFree(m->d_ent);
+  cudaFree(m->d_fbw);
+  cudaFree(m->d_slot);
   delete m;
 }
 
@@ -406,18 +446,19 @@ extern "C" int e2e_mel_forward(e2e_mel* m, const float* wav, int32_t B, int64_t 
   p.n_mels = m->n_mels;
   p.nnz = m->nnz;
   p.nb = m->nb;
-  p.fb_per = m->fb_per;
+  p.fb_split = m->split;
   p.mel = mel;
   p.energy = energy;
   p.range_flag = range_flag;
   p.window = m->d_window;
   p.tw = m->d_tw;
-  p.fb_ent = m->d_ent;
+  p.fb_w = m->d_fbw;
+  p.fb_slot = m->d_slot;
   dim3 grid((unsigned)((T + kF - 1) / kF), (unsigned)B);
-  if (m->fb_per == 13)
-    mel_kernel<13><<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  if (m->variant == 0)
+    mel_kernel<6, 5><<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   else
-    mel_kernel<kFbPerMax><<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    mel_kernel<8, 8><<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("mel_kernel launch: ") + cudaGetErrorString(e));
   return 0;

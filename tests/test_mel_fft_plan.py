@@ -93,25 +93,33 @@ def test_parseval_energy_identity():
         np.testing.assert_allclose(lhs, rhs, rtol=1e-12)
 
 
-def test_filterbank_split_is_exact_and_bounded():
-    """Mirror of e2e_mel_create's sparse filterbank split (mel.cu): the non-zeros in (filter, bin) order are cut
-    into 64 runs of PER entries; every thread leaves one partial per filter it touched; fixed-order sums reproduce
-    basis @ mag, and no filter spreads over more than kFbSplit = 8 threads."""
+def test_filterbank_block_form_is_exact_and_fits():
+    """Mirror of e2e_mel_create's sparse filterbank (mel.cu): thread t of a frame owns bins [6t, 6t + 6) and the filters
+    overlapping them as a dense 5 x 6 block; one partial per (filter, thread); fixed-order sums reproduce basis @ mag.
+    Checks the bounds the kernel variant <BPT = 6, FPB = 5> relies on for the e2e-tts basis."""
     from oracle import mel_oracle as mo
     basis = mo.slaney_mel_basis().astype(np.float64)
-    n_mels = basis.shape[0]
-    ents = [(basis[r, k], r, k) for r in range(n_mels) for k in range(basis.shape[1]) if basis[r, k] != 0.0]
-    assert len(ents) <= 64 * 17
-    per = 13 if len(ents) <= 64 * 13 else 17            # the two instantiations of mel_kernel<PER>
+    n_mels, nbins = basis.shape
+    nb = 1 + max(k for k in range(nbins) if basis[:, k].any())
+    assert nb == 372 and 64 * 6 >= nb                      # bins the kernel computes magnitudes for
+    BPT, FPB = 6, 5
     rng = np.random.default_rng(3)
-    mag = rng.uniform(0, 10, basis.shape[1])
-    first, nthr, part = {}, {}, {}
+    mag = rng.uniform(0, 10, nbins)
+    first, count, part = {}, {}, {}
     for t in range(64):
-        for (w, r, k) in ents[t * per:(t + 1) * per]:
+        bins = [k for k in range(t * BPT, (t + 1) * BPT) if k < nbins]
+        filt = [r for r in range(n_mels) if basis[r, bins].any()]
+        assert len(filt) <= FPB
+        for r in filt:
             first.setdefault(r, t)
-            nthr[r] = t - first[r] + 1
-            part[(r, t - first[r])] = part.get((r, t - first[r]), 0.0) + w * mag[k]
-    assert max(nthr.values()) <= 8
-    got = np.array([sum(part[(r, q)] for q in range(nthr[r])) for r in range(n_mels)])
+            count[r] = t - first[r] + 1
+            part[(r, t - first[r])] = sum(basis[r, k] * mag[k] for k in bins)
+    split = max(count.values())
+    assert split <= 12
+    got = np.array([sum(part.get((r, q), 0.0) for q in range(split)) for r in range(n_mels)])
     np.testing.assert_allclose(got, basis @ mag, rtol=1e-12)
-    assert 1 + max(k for (_, _, k) in ents) == 372          # bins the kernel computes magnitudes for
+    # padded magnitude index: pitch 7 per 6-bin block keeps the 64 threads on distinct banks
+    pad = lambda k: k + (k // BPT) * ((BPT | 1) - BPT)
+    assert len({pad(k) for k in range(384)}) == 384 and max(pad(k) for k in range(384)) < 584
+    for i in range(BPT):
+        assert len({(t * 7 + i) % 32 for t in range(32)}) == 32
