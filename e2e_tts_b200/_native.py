@@ -47,6 +47,12 @@ SYMBOLS = {
     "e2e_voc_set_profile_events": (c_int, [c_void_p, c_void_p, c_void_p]),
     "e2e_voc_hop": (c_int, [c_void_p]),
     "e2e_voc_launches_per_forward": (c_int, [c_void_p]),
+    "e2e_postnet_create": (c_int, [c_int32, c_int32, c_int32, c_int32, POINTER(c_void_p)]),
+    "e2e_postnet_destroy": (None, [c_void_p]),
+    "e2e_postnet_load_layer": (c_int, [c_void_p, c_int32, POINTER(c_float), c_int64, POINTER(c_float), c_int64]),
+    "e2e_postnet_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
+    "e2e_postnet_forward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
+                                    c_void_p]),
     "e2e_mel_create": (c_int, [c_int32, c_int32, c_int32, c_int32, POINTER(c_float), POINTER(c_void_p)]),
     "e2e_mel_destroy": (None, [c_void_p]),
     "e2e_mel_num_frames": (c_int64, [c_void_p, c_int64]),

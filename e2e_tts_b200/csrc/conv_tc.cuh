@@ -64,6 +64,7 @@ struct ConvParams {
   int n_units;          // B * tiles_per_b * n_tiles
   float divisor;        // epilogue: 0 = none, else out /= divisor (generator.py:48, xs / num_kernels)
   float slope;          // LeakyReLU slope applied to out_act
+  int act_tanh;         // 1: out_act = tanh(result) instead (Postnet)
   int8_t shift[kMaxNTiles][kMaxTaps];  // row shift of each tap, per N tile
   const uint8_t* w;     // packed weights
   const float* bias;    // [n_total]
@@ -358,6 +359,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     eo.slope = p.slope;
     eo.scale = p.divisor != 0.f ? 1.0f / p.divisor : 0.f;
     eo.inv = p.res_inv_slope;
+    eo.act_tanh = p.act_tanh;
     uint32_t it = 0, acc = 0, apar = 0;
     UnitIter uit;
     uit.init(u_first, u_step, p.n_tiles, p.tiles_per_b);

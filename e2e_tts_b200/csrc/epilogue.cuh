@@ -64,6 +64,7 @@ struct EpiOut {
   float* out_f32;
   __nv_bfloat16* out_act;
   float slope, scale, inv;  // scale: 0 = none, else result *= scale (1 / num_kernels)
+  int act_tanh;             // out_act = bf16(tanh(result)) instead of leaky_relu (Postnet, N2)
 };
 
 __device__ __forceinline__ void add_bf16x16(float (&f)[16], const uint4 (&q)[2]) {
@@ -118,11 +119,19 @@ __device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const floa
   if (o.out_act) {
     const float s = o.slope;
     uint32_t pk[8];
+    if (o.act_tanh) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float a = f[2 * i], c = f[2 * i + 1];
-      __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, a * s), fmaxf(c, c * s));  // leaky_relu, 0 < s <= 1
-      pk[i] = *reinterpret_cast<uint32_t*>(&h);
+      for (int i = 0; i < 8; ++i) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(tanhf(f[2 * i]), tanhf(f[2 * i + 1]));
+        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float a = f[2 * i], c = f[2 * i + 1];
+        __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, a * s), fmaxf(c, c * s));  // leaky_relu, 0 < s <= 1
+        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+      }
     }
     st_global_256(o.out_act + off, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
   }

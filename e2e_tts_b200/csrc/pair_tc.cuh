@@ -331,6 +331,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     eo.slope = p.slope;
     eo.scale = p.divisor != 0.f ? 1.0f / p.divisor : 0.f;
     eo.inv = p.res_inv_slope;
+    eo.act_tanh = 0;
     const float smid = p.slope_mid;
     E2E_TR2_DECL
 

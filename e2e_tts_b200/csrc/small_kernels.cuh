@@ -160,6 +160,20 @@ post_conv_tanh_generic_kernel(const __nv_bfloat16* __restrict__ act, const float
   }
 }
 
+// ---- Postnet tail (N2): y [B][T][ldy] fp32 (channels-last GEMM output, ldy >= C) -> out [B][T][C] fp32, optionally
+// + x (the caller's `postnet(output) + output`, unsupervised_fastspeech2/model.py:188) ----
+__global__ void __launch_bounds__(256)
+postnet_out_kernel(const float* __restrict__ y, const float* __restrict__ x, long long total, int C, int ldy,
+                   float* __restrict__ out) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long row = idx / C;
+  const int c = (int)(idx - row * C);
+  float v = y[row * ldy + c];
+  if (x) v += x[idx];
+  out[idx] = v;
+}
+
 // ---- iSTFTNet head (class iSTFT, generator.py:91-109) ----
 // ReflectionPad1d((1, 0)) on channels-last rows: out[b][0] = in[b][1], out[b][p] = in[b][p-1]; 16 bytes per thread.
 __global__ void __launch_bounds__(256)

@@ -653,5 +653,145 @@ extern "C" int e2e_istft_forward(const float* mag, const float* phase, int32_t B
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// N2 (SURVEY.md §8 f): the acoustic model's Postnet, the step right before the vocoder
+// (e2e_tts/models/acoustic/unsupervised_fastspeech2/layers.py:507-563): conv_layers x [Conv1d(k) -> BatchNorm1d (eval:
+// folded into the conv by the caller) -> tanh (all but the last)], on [B, T, C] channels-last input - the layout the
+// implicit-GEMM kernel wants, so the reference's two transposes disappear.  Same conv_tc kernel, tanh epilogue.
+// ---------------------------------------------------------------------------------------------------
+struct e2e_postnet {
+  e2e_voc core;   // layer table, packed weights, plans
+  int C = 0, H = 0, n_layers = 0, k = 0, c_pad = 0, out_pad = 0;
+};
+
+extern "C" int e2e_postnet_create(int32_t n_channels, int32_t embedding_dim, int32_t conv_layers, int32_t kernel_size,
+                                  e2e_postnet** out) {
+  if (!out) return fail(-1, "null argument");
+  if (n_channels < 1 || n_channels > 256 || embedding_dim % 64 != 0 || embedding_dim < 64 || embedding_dim > 512)
+    return fail(-4, "postnet: n_channels in [1, 256], embedding_dim a multiple of 64 <= 512");
+  if (conv_layers < 2 || conv_layers > 16 || !(kernel_size & 1) || kernel_size > kMaxTaps)
+    return fail(-4, "postnet: 2..16 layers, odd kernel size <= 15");
+  std::unique_ptr<e2e_postnet> pn(new e2e_postnet);
+  pn->C = n_channels;
+  pn->H = embedding_dim;
+  pn->n_layers = conv_layers;
+  pn->k = kernel_size;
+  pn->c_pad = (n_channels + 63) / 64 * 64;
+  pn->out_pad = (n_channels + 31) / 32 * 32;
+  e2e_voc* v = &pn->core;
+  v->cfg = e2e_voc_config{};
+  v->cfg.in_channels = n_channels;
+  v->cfg.upsample_initial_channel = embedding_dim;
+  v->cin_pad = pn->c_pad;
+  for (int i = 0; i < conv_layers; ++i) {
+    const int cin = i == 0 ? n_channels : embedding_dim, cin_pad = i == 0 ? pn->c_pad : embedding_dim;
+    const bool last = i + 1 == conv_layers;
+    add_conv(v, "convolutions." + std::to_string(i), cin, cin_pad, last ? n_channels : embedding_dim, kernel_size, 1,
+             last ? pn->out_pad : 0);
+  }
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail((int)e, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
+  cudaDeviceGetAttribute(&v->n_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (v->n_sms < 1) v->n_sms = 148;
+  int rc = conv_kernels_init();
+  if (rc) return rc;
+  *out = pn.release();
+  return 0;
+}
+
+extern "C" void e2e_postnet_destroy(e2e_postnet* pn) {
+  if (!pn) return;
+  for (auto& L : pn->core.layers) {
+    if (L.d_w) cudaFree(L.d_w);
+    if (L.d_bias) cudaFree(L.d_bias);
+  }
+  delete pn;
+}
+
+extern "C" int e2e_postnet_load_layer(e2e_postnet* pn, int32_t index, const float* weight, int64_t weight_numel,
+                                      const float* bias, int64_t bias_numel) {
+  if (!pn) return fail(-1, "null argument");
+  return e2e_voc_load_layer(&pn->core, ("convolutions." + std::to_string(index)).c_str(), weight, weight_numel, bias,
+                            bias_numel);
+}
+
+static void postnet_carve(const e2e_postnet* pn, int B, int T, void* ws, __nv_bfloat16** xin, __nv_bfloat16** h0,
+                          __nv_bfloat16** h1, float** y, size_t* total) {
+  uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* r = p ? p + off : nullptr;
+    off += align_up(bytes, 1024);
+    return r;
+  };
+  const size_t rows = (size_t)B * T;
+  *xin = (__nv_bfloat16*)take(rows * pn->c_pad * 2);
+  *h0 = (__nv_bfloat16*)take(rows * pn->H * 2);
+  *h1 = (__nv_bfloat16*)take(rows * pn->H * 2);
+  *y = (float*)take(rows * pn->out_pad * 4);
+  *total = off;
+}
+
+extern "C" size_t e2e_postnet_workspace_bytes(const e2e_postnet* pn, int32_t B, int32_t T) {
+  if (!pn || B < 1 || T < 1) return 0;
+  __nv_bfloat16 *a, *b, *c;
+  float* y;
+  size_t total;
+  postnet_carve(pn, B, T, nullptr, &a, &b, &c, &y, &total);
+  return total;
+}
+
+extern "C" int e2e_postnet_forward(e2e_postnet* pn, const float* x, int32_t B, int32_t T, int32_t add_input, float* out,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  if (!pn || !x || !out || !workspace) return fail(-1, "null argument");
+  if (B < 1 || T < 1) return fail(-1, "B and T must be positive");
+  e2e_voc* v = &pn->core;
+  if (e2e_voc_missing_layers(v) != 0) return fail(-7, "e2e_postnet_forward before all layers were loaded");
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(-1, "workspace must be 1024-byte aligned");
+  if (workspace_bytes < e2e_postnet_workspace_bytes(pn, B, T)) return fail(-1, "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16 *xin, *h0, *h1;
+  float* y;
+  size_t total;
+  postnet_carve(pn, B, T, workspace, &xin, &h0, &h1, &y, &total);
+  PlanKey key{B, T, workspace};
+  auto it = v->plans.find(key);
+  if (it == v->plans.end()) {
+    std::vector<Op> ops;
+    const __nv_bfloat16* in = xin;
+    for (int i = 0; i < pn->n_layers; ++i) {
+      const bool last = i + 1 == pn->n_layers;
+      __nv_bfloat16* o = (i & 1) ? h1 : h0;
+      int rc = make_conv_op(v, ops, v->by_name["convolutions." + std::to_string(i)], B, T, in, nullptr, nullptr,
+                            last ? y : nullptr, last ? nullptr : o, 1.0f, 0.f);
+      if (rc) return rc;
+      ops.back().plan.p.act_tanh = last ? 0 : 1;   // torch.tanh(self.convolutions[i](x)), layers.py:558-559
+      in = o;
+    }
+    if (v->plans.size() > 64) v->plans.clear();
+    it = v->plans.emplace(key, std::move(ops)).first;
+  }
+  // [B, T, C] fp32 is element (b, c, t) at x[b*T*C + c + t*C]: the [B,80,T]-view kernel does the bf16 / padding pass
+  {
+    const long long tot = (long long)B * T * (pn->c_pad / 8);
+    mel_to_act_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, (long long)T * pn->C, 1, pn->C, B, T, pn->C,
+                                                                    pn->c_pad, xin);
+  }
+  for (const Op& op : it->second) {
+    int rc = launch_conv(op.plan, st);
+    if (rc) return rc;
+  }
+  {
+    const long long tot = (long long)B * T * pn->C;
+    postnet_out_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(y, add_input ? x : nullptr, tot, pn->C, pn->out_pad,
+                                                                     out);
+  }
+  v->last_launches = (int)it->second.size() + 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, std::string("e2e_postnet_forward launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
 extern "C" const char* e2e_last_error_string(void) { return last_error().c_str(); }
 extern "C" const char* e2e_version_string(void) { return "e2e_tts_b200 0.1 sm_100a"; }

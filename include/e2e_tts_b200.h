@@ -104,6 +104,23 @@ int e2e_voc_hop(const e2e_voc* v);
 /* Kernel launches enqueued by one e2e_voc_forward call at the current configuration. */
 int e2e_voc_launches_per_forward(const e2e_voc* v);
 
+/* ---- Postnet (N2, the step right before the vocoder) ----
+ * Replaces Postnet.forward (e2e_tts/models/acoustic/unsupervised_fastspeech2/layers.py:507-563) in eval mode:
+ * conv_layers x [Conv1d(kernel_size, same padding) -> BatchNorm1d -> tanh (all but the last)] on [B, T, n_channels].
+ * e2e_postnet_load_layer takes layer `index`'s conv weight [C_out][C_in][k] / bias with the BatchNorm1d running
+ * statistics already folded in (w * g/sqrt(var+eps), (b - mean) * g/sqrt(var+eps) + beta), fp32 on the HOST.
+ * x, out: device fp32 [B][T][n_channels] contiguous; add_input != 0 fuses the caller's `postnet(output) + output`
+ * (model.py:188). */
+typedef struct e2e_postnet e2e_postnet;
+int e2e_postnet_create(int32_t n_channels, int32_t embedding_dim, int32_t conv_layers, int32_t kernel_size,
+                       e2e_postnet** out);
+void e2e_postnet_destroy(e2e_postnet* pn);
+int e2e_postnet_load_layer(e2e_postnet* pn, int32_t index, const float* weight, int64_t weight_numel,
+                           const float* bias, int64_t bias_numel);
+size_t e2e_postnet_workspace_bytes(const e2e_postnet* pn, int32_t B, int32_t T);
+int e2e_postnet_forward(e2e_postnet* pn, const float* x, int32_t B, int32_t T, int32_t add_input, float* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- mel front-end ---- */
 typedef struct e2e_mel e2e_mel; /* opaque: window, twiddles and the sparse mel filterbank on the device */
 

@@ -122,6 +122,23 @@ def main() -> None:
     print("istft_strong: frames=%d oracle-vs-reference log-spec err=%.3g phase err=%.3g" % (spec.shape[-1], e1[0], e1[1]))
     assert max(e1) < 1e-4
 
+    # Postnet (N2): the reference class in eval mode vs the oracle restatement
+    from . import postnet_oracle as pno
+    sys.path.insert(0, REF)
+    from models.acoustic.unsupervised_fastspeech2.layers import Postnet  # noqa
+    psd = pno.make_state_dict(80, pno.DEFAULT_CONFIG, 41)
+    pref = Postnet(n_channels=80, config=pno.DEFAULT_CONFIG)
+    pref.load_state_dict(psd)
+    pref.eval()
+    px = mel_like(2, 37, 141).transpose(1, 2).contiguous()          # [B, T, 80], log-mel-like values
+    with torch.no_grad():
+        pwant = pref(px)
+        pgot = pno.postnet_forward(psd, pno.DEFAULT_CONFIG, px)
+    perr = (pgot - pwant).abs().max().item()
+    print("postnet_default: |ref|max=%.3f oracle-vs-reference max abs err=%.3g" % (pwant.abs().max().item(), perr))
+    assert perr < 1e-4
+    np.savez_compressed(os.path.join(OUT, "postnet_default.npz"), x=px.numpy(), y=pwant.numpy(), seed=41)
+
     TorchSTFT, generate_melspecs = _import_reference_stft()
     from tools.stft import inverse_stft  # noqa
     with torch.no_grad():
