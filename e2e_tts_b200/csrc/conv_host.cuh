@@ -170,6 +170,13 @@ inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pr
   return fail(-3, "convolution does not fit shared memory / TMEM");
 }
 
+// E2E_NO_PDL=1 launches every kernel fully serialised (A/B experiments).
+inline bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) on = std::getenv("E2E_NO_PDL") ? 0 : 1;
+  return on == 1;
+}
+
 typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const ConvParams);
 
 inline ConvKernelFn conv_kernel_for(int rowb, int mt, int cg = 1) {
@@ -214,13 +221,15 @@ inline int launch_conv(const ConvPlan& plan, cudaStream_t st) {
   cfg.blockDim = dim3(kConvThreads, 1, 1);
   cfg.dynamicSmemBytes = plan.smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = plan.cg;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddep_wait() in ptx.cuh
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, conv_kernel_for(plan.p.rowb, plan.p.mt, plan.cg), plan.tm, plan.tm_w, plan.p);
   if (e != cudaSuccess) return fail((int)e, std::string("conv_tc launch: ") + cudaGetErrorString(e));
   e = cudaGetLastError();

@@ -194,10 +194,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) E2E_TR(1);
+  griddep_launch();  // the next layer's CTAs may take this SM as soon as this CTA exits
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- panel producer (TMA) ----------------
+      griddep_wait();  // the activations are the previous kernel's output
       constexpr int ch_per_panel = ROWB / 2;
       const int boxes = p.slab_rows / p.box_rows;
       uint32_t slot = 0, par = 1;  // ring position; `par` is the parity a fresh/recycled slot is waited on
@@ -346,6 +348,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     if (leader) E2E_TR(4);
   } else if (warp >= 4) {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
+    griddep_wait();  // residual / running-sum reads and every output store follow the previous kernel
     const int e = warp - 4;
     const int quarter = e & 3;  // == warp % 4: the TMEM lanes this warp may read
     const int part = e >> 2;    // this warp takes the items with item % 4 == part

@@ -127,13 +127,15 @@ inline int launch_pair(const PairPlan& plan, cudaStream_t st) {
   cfg.blockDim = dim3(kConvThreads, 1, 1);
   cfg.dynamicSmemBytes = plan.smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = plan.cg;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddep_wait() in ptx.cuh
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, pair_kernel_for(plan.rowb, plan.mt, plan.cg), plan.tm, plan.tm_w1, plan.tm_w2,
                                      plan.p);
   if (e != cudaSuccess) return fail((int)e, std::string("pair_tc launch: ") + cudaGetErrorString(e));

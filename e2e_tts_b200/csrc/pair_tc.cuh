@@ -149,10 +149,12 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) E2E_TR(1);
+  griddep_launch();  // the next layer's CTAs may take this SM as soon as this CTA exits
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- input slab producer (TMA) ----------------
+      griddep_wait();  // the activations are the previous kernel's output
       const int boxes = p.a_rows / p.box_rows;
       UnitIter uit;
       uit.init(u_first, u_step, 1, p.tiles_per_b);
@@ -314,6 +316,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     if (leader) E2E_TR(4);
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
+    griddep_wait();  // residual / running-sum reads and every output store follow the previous kernel
     const int e = warp - 4;
     const int quarter = e & 3;
     const int part = e >> 2;

@@ -186,6 +186,16 @@ __device__ __forceinline__ void setmaxnreg_inc() {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start (CTA by CTA, as SMs free up) before the previous kernel of the stream has finished.  griddep_wait() blocks
+// until that previous grid has completed and its memory is visible: every role calls it before its first access to
+// an activation tensor, so barrier init, TMEM allocation, descriptor prefetch and the first weight tiles overlap the
+// previous layer's tail.  griddep_launch() lets the NEXT kernel start early in the same way.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------
 // Proxy / tcgen05 fences
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
