@@ -144,3 +144,22 @@ def test_forward_pcm16_is_the_callers_post_processing_fused():
     assert np.array_equal(pkg.combine_audio(list(pcm.cpu()), lengths, 100), ref_stream)
     with pytest.raises(ValueError):
         voc.forward_pcm16(mel, [1, 2])
+
+
+def test_empty_inputs_and_size_guards():
+    """Empty batches / zero frames return empty waveforms (the reference's convs do the same for B = 0); utterances
+    whose waveform index would not fit 31 bits are refused with a Python exception, not a crash."""
+    voc, _ = build(ho.DEFAULT_CONFIG, 12, "strong")
+    with torch.no_grad():
+        assert voc(torch.zeros(0, 80, 5).cuda()).shape == (0, 1, 1280)
+        assert voc(torch.zeros(2, 80, 0).cuda()).shape == (2, 1, 0)
+        assert voc.forward_pcm16(torch.zeros(0, 80, 5).cuda()).shape == (0, 1280)
+        voc(torch.zeros(1, 80, 3).cuda())                               # creates the native handle
+    from e2e_tts_b200 import _native
+    lib = _native.lib()
+    rc = lib.e2e_voc_forward(voc._handle, 8, 1, 1, 1, 1, 1 << 23, 8, 1024, 1 << 40, None)   # T * 256 >= 2^31
+    assert rc != 0 and b"too long" in lib.e2e_last_error_string()
+    with pytest.raises(ValueError):
+        voc(torch.zeros(1, 81, 4).cuda())
+    with pytest.raises(ValueError):
+        voc(torch.zeros(1, 80, 4, dtype=torch.float64).cuda())
