@@ -8,6 +8,8 @@ It is a plain fp32 (or fp64) restatement, in eager torch-on-CPU functional ops, 
     e2e_tts/models/vocoder/layers.py:33-40      ResBlock1.forward
     e2e_tts/models/vocoder/layers.py:60-65      ResBlock2.forward
     e2e_tts/models/vocoder/function.py:16-17    get_padding
+    e2e_tts/models/vocoder/generator.py:91-109  iSTFT.forward (istft_forward; `resblock == '1'` quirk of :71 included)
+    e2e_tts/src/tools/stft.py:138-148           inverse_stft (+ inverse_stft_def, a float64 numpy definition)
 plus the weight-norm fold torch applies in its pre-forward hook (w = g * v / ||v||, norm over all dims but 0).
 A second, definition-level numpy implementation of the two convolutions (`conv1d_def`,
 `conv_transpose1d_def`, SURVEY.md §8 a'5-6) cross-checks the torch ops on tiny shapes.
