@@ -12,6 +12,7 @@ from .stft import TorchSTFT, generate_melspecs, inverse_stft, dynamic_range_comp
 
 from .postprocess import combine_audio  # noqa: F401
 from .postnet import Postnet  # noqa: F401
+from .serving import HostPipeline  # noqa: F401
 
-__all__ = ["combine_audio", "Postnet", "HifiGan", "iSTFT", "inverse_stft", "ResBlock1", "ResBlock2", "get_padding", "init_weights", "TorchSTFT", "generate_melspecs",
+__all__ = ["combine_audio", "Postnet", "HostPipeline", "HifiGan", "iSTFT", "inverse_stft", "ResBlock1", "ResBlock2", "get_padding", "init_weights", "TorchSTFT", "generate_melspecs",
            "dynamic_range_compression", "dynamic_range_decompression"]

@@ -284,8 +284,16 @@ class HifiGan(nn.Module):
         if p0.device != x.device:
             raise RuntimeError("module parameters are on %s but the input is on %s" % (p0.device, x.device))
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """generator.py:37-53.  x: [B, 80, T] float32 CUDA tensor (non-contiguous views are fine)."""
+    def _check_out(self, out, shape, dtype, device):
+        if out is None:
+            return torch.empty(shape, dtype=dtype, device=device)
+        if tuple(out.shape) != tuple(shape) or out.dtype != dtype or out.device != device or not out.is_contiguous():
+            raise ValueError("out must be a contiguous %s tensor of shape %s on %s" % (dtype, tuple(shape), device))
+        return out
+
+    def forward(self, x: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+        """generator.py:37-53.  x: [B, 80, T] float32 CUDA tensor (non-contiguous views are fine).  `out` (not in the
+        reference): an optional preallocated [B, 1, hop*T] float32 result tensor (serving loops, HostPipeline)."""
         self._check_input(x)
         B, _, T = x.shape
         if B == 0 or T == 0:
@@ -294,7 +302,7 @@ class HifiGan(nn.Module):
             self._sync_native(x.device)
             ws = self._workspace(B, T, x.device)
             ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
-            out = torch.empty((B, 1, self.hop * T), dtype=torch.float32, device=x.device)
+            out = self._check_out(out, (B, 1, self.hop * T), torch.float32, x.device)
             stream = torch.cuda.current_stream(x.device).cuda_stream
             if self._profile_events is not None:   # bench.py: time the tensor-core segment of this call
                 ev0, ev1 = self._profile_events
@@ -307,7 +315,8 @@ class HifiGan(nn.Module):
             _native.check(rc, "e2e_voc_forward")
         return out
 
-    def forward_pcm16(self, x: torch.Tensor, mel_lengths=None, max_wav_value: float = 32768.0) -> torch.Tensor:
+    def forward_pcm16(self, x: torch.Tensor, mel_lengths=None, max_wav_value: float = 32768.0,
+                      out: torch.Tensor = None) -> torch.Tensor:
         """forward() fused with the caller's post-processing (combine_audio, e2e_tts/src/api/utils.py:108-117):
         returns int16 PCM [B, hop*T] = trunc(wav * max_wav_value), zero beyond mel_lengths[b] * hop.  Half the
         device->host (and multi-GPU gather) bytes of forward().  mel_lengths: None, a sequence, or an int tensor [B]."""
@@ -324,7 +333,7 @@ class HifiGan(nn.Module):
             self._sync_native(x.device)
             ws = self._workspace(B, T, x.device)
             ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
-            out = torch.empty((B, self.hop * T), dtype=torch.int16, device=x.device)
+            out = self._check_out(out, (B, self.hop * T), torch.int16, x.device)
             stream = torch.cuda.current_stream(x.device).cuda_stream
             rc = _native.lib().e2e_voc_forward_pcm16(self._handle, x.data_ptr(), x.stride(0), x.stride(1), x.stride(2),
                                                      B, T, lens.data_ptr() if lens is not None else None,

@@ -163,3 +163,25 @@ def test_empty_inputs_and_size_guards():
         voc(torch.zeros(1, 81, 4).cuda())
     with pytest.raises(ValueError):
         voc(torch.zeros(1, 80, 4, dtype=torch.float64).cuda())
+
+
+def test_host_pipeline_matches_direct_calls():
+    """e2e_tts_b200.HostPipeline (pinned host in / out, copies overlapped with synthesis) returns exactly what the
+    direct forward() / forward_pcm16() calls return, for more batches than it has buffers."""
+    voc, _ = build(ho.DEFAULT_CONFIG, 14, "strong")
+    mels = [mel_like(2, 30, 50 + i).pin_memory() for i in range(5)]
+    outs = [torch.empty(2, 30 * 256).pin_memory() for _ in range(5)]
+    pipe = pkg.HostPipeline(voc)
+    for m, o in zip(mels, outs):
+        pipe.submit(m, o)
+    pipe.drain()
+    with torch.no_grad():
+        for m, o in zip(mels, outs):
+            assert torch.equal(o, voc(m.cuda()).squeeze(1).cpu())
+    pcm = [torch.empty(2, 30 * 256, dtype=torch.int16).pin_memory() for _ in range(3)]
+    pipe16 = pkg.HostPipeline(voc.forward_pcm16)
+    idx = [pipe16.submit(m, o) for m, o in zip(mels[:3], pcm)]
+    pipe16.wait(idx[-1])
+    with torch.no_grad():
+        for m, o in zip(mels[:3], pcm):
+            assert torch.equal(o, voc.forward_pcm16(m.cuda()).cpu())
