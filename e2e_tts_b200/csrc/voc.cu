@@ -540,6 +540,7 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
     return fail(-1, "this generator has the HiFi-GAN head: call e2e_voc_forward / e2e_voc_forward_pcm16");
   }
   if (B < 1 || T < 1) return fail(-1, "B and T must be positive");
+  if (B > 65535) return fail(-1, "at most 65535 utterances per call (split the batch)");
   if ((long long)T * v->hop > 0x7fffffffLL) return fail(-1, "utterance too long");
   if (e2e_voc_missing_layers(v) != 0) return fail(-7, "e2e_voc_forward before all layers were loaded");
   if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(-1, "workspace must be 1024-byte aligned");
