@@ -209,9 +209,11 @@ def main():
     wav_host = torch.empty((B, S), dtype=torch.float32).pin_memory()
     gathered = torch.empty((world * B, S), dtype=torch.float32, device=dev) if (world > 1 and rank == 0) else None
 
+    out_dev = torch.empty((B, 1, S), dtype=torch.float32, device=dev)
+
     def step(i):
         with torch.no_grad():
-            wav = voc(mels_dev[i % n_in]).squeeze(1)
+            wav = voc(mels_dev[i % n_in], out=out_dev).squeeze(1)
             if world > 1:   # final gather of waveforms on rank 0 over NVLink (part of the step)
                 dist.gather(wav, list(gathered.split(B)) if rank == 0 else None, dst=0)
         return wav
