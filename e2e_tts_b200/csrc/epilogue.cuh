@@ -76,6 +76,62 @@ __device__ __forceinline__ void add_bf16x16(float (&f)[16], const uint4 (&q)[2])
   }
 }
 
+// 16-byte shared-memory accesses by shared-window address
+__device__ __forceinline__ void st_shared_u4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// named barrier over `nthreads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// acc + bias + residual (+ partial sums) (* scale) -> leaky_relu -> 16 bf16 (8 packed words), for one 16-column item:
+// the arithmetic of epi_finish16 without the stores (the fused pair kernel stages the result in shared memory and
+// writes it to global memory with coalesced accesses).
+__device__ __forceinline__ void epi_compute16(const uint32_t (&v)[16], const float4 (&bv)[4], const uint4 (&rq)[2],
+                                              const uint4 (&sa)[2], const EpiOut& o, uint32_t (&pk)[8]) {
+  float f[16];
+  const uint32_t w[8] = {rq[0].x, rq[0].y, rq[0].z, rq[0].w, rq[1].x, rq[1].y, rq[1].z, rq[1].w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+    f[2 * j] = fminf(lo, lo * o.inv);
+    f[2 * j + 1] = fminf(hi, hi * o.inv);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[4 * i] += __uint_as_float(v[4 * i]) + bv[i].x;
+    f[4 * i + 1] += __uint_as_float(v[4 * i + 1]) + bv[i].y;
+    f[4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bv[i].z;
+    f[4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bv[i].w;
+  }
+  if (o.sum_a) {
+    const uint32_t q[8] = {sa[0].x, sa[0].y, sa[0].z, sa[0].w, sa[1].x, sa[1].y, sa[1].z, sa[1].w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[2 * j] += __uint_as_float(q[j] << 16);
+      f[2 * j + 1] += __uint_as_float(q[j] & 0xffff0000u);
+    }
+  }
+  if (o.scale != 0.f) {
+    const float sc = o.scale;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] *= sc;
+  }
+  const float s = o.slope;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float a = f[2 * i], c = f[2 * i + 1];
+    __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, a * s), fmaxf(c, c * s));  // leaky_relu, 0 < s <= 1
+    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+
 // acc + bias + residual (+ partial sums) (* scale) -> out_f32 and/or leaky_relu -> out_act, for one 16-column item.
 //   v        raw accumulator bits
 //   bv       bias of the 16 columns
