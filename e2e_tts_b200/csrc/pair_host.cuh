@@ -10,10 +10,12 @@ struct PairPlan {
   PairParams p{};
   CUtensorMap tm{};            // input activation [B][T][C]
   CUtensorMap tm_w1{}, tm_w2{};  // packed weight images as [rows][rowb] matrices (CTA-pair form only)
+  CUtensorMap tm_out{}, tm_out2{};  // output activation [B][T][C]: boxes of min(r_out, 256) / r_out - 256 rows
   dim3 grid{};
   int smem_bytes = 0;
   int rowb = 128, mt = 1;
   int cg = 1;                  // CTAs per MMA (tcgen05 cta_group): 2 = CTA pairs in 2-CTA clusters
+  bool staged = false;         // c2 epilogue staged in shared memory + TMA store (see pair_tc.cuh)
 };
 
 // CTA pairs pay off where the MMAs dominate and the one-CTA form is bound by shared-memory traffic (B operand
@@ -43,6 +45,10 @@ inline int plan_pair(PairPlan& plan, int C, int k, int d, int B, int T, int n_sm
   plan.rowb = C == 32 ? 64 : 128;
   plan.mt = 128 / C;
   plan.cg = pair_cta_group(C, k);
+  {
+    const char* e = std::getenv("E2E_PAIR_STAGED");   // 0 | 1 overrides for experiments
+    plan.staged = e ? (e[0] == '1' && C >= 64) : (C >= 64 && k <= 3);
+  }
   const int rowb = plan.rowb, mt = plan.mt, cg = plan.cg;
   p.T = T;
   p.B = B;
@@ -93,15 +99,28 @@ inline int pair_weight_maps(PairPlan& plan, const void* w1, const void* w2) {
   return make_weight_tensor_map(&plan.tm_w2, w2, rows, plan.rowb, p.nt / 2);
 }
 
-typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const PairParams);
+// Fills plan.tm_out / tm_out2: the result tile of a unit (r_out rows) leaves shared memory as TMA stores of one
+// 64-channel (or 32-channel) panel each; a box is at most 256 rows high, so tall units (C = 32: r_out ~ 500) use a
+// second map for the rows past 256 (its shared-memory source starts on an 8-row boundary, as the swizzle needs).
+inline int pair_output_maps(PairPlan& plan, const void* out, int B, int T, int C) {
+  const int r1 = plan.p.r_out < 256 ? plan.p.r_out : 256;
+  int rc = make_act_tensor_map(&plan.tm_out, out, B, T, C, plan.rowb / 2, r1);
+  if (rc) return rc;
+  const int r2 = plan.p.r_out - r1;
+  return make_act_tensor_map(&plan.tm_out2, out, B, T, C, plan.rowb / 2, r2 > 0 ? r2 : 8);
+}
 
-inline PairKernelFn pair_kernel_for(int rowb, int mt, int cg) {
-  if (cg == 2) {
-    if (rowb == 64) return pair_tc_kernel<64, 4, 2>;
-    return mt == 2 ? pair_tc_kernel<128, 2, 2> : pair_tc_kernel<128, 1, 2>;
+typedef void (*PairKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                             const CUtensorMap, const PairParams);
+
+inline PairKernelFn pair_kernel_for(int rowb, int mt, int cg, bool staged = false) {
+  if (rowb == 64) return cg == 2 ? pair_tc_kernel<64, 4, 2, false> : pair_tc_kernel<64, 4, 1, false>;
+  if (staged) {
+    if (cg == 2) return mt == 2 ? pair_tc_kernel<128, 2, 2, true> : pair_tc_kernel<128, 1, 2, true>;
+    return mt == 2 ? pair_tc_kernel<128, 2, 1, true> : pair_tc_kernel<128, 1, 1, true>;
   }
-  if (rowb == 64) return pair_tc_kernel<64, 4, 1>;
-  return mt == 2 ? pair_tc_kernel<128, 2, 1> : pair_tc_kernel<128, 1, 1>;
+  if (cg == 2) return mt == 2 ? pair_tc_kernel<128, 2, 2, false> : pair_tc_kernel<128, 1, 2, false>;
+  return mt == 2 ? pair_tc_kernel<128, 2, 1, false> : pair_tc_kernel<128, 1, 1, false>;
 }
 
 inline int pair_kernels_init() {
@@ -109,8 +128,11 @@ inline int pair_kernels_init() {
   int dev = 0;
   cudaGetDevice(&dev);
   if (done_for_device == dev) return 0;
-  PairKernelFn fns[6] = {pair_tc_kernel<64, 4, 1>, pair_tc_kernel<128, 2, 1>, pair_tc_kernel<128, 1, 1>,
-                         pair_tc_kernel<64, 4, 2>, pair_tc_kernel<128, 2, 2>, pair_tc_kernel<128, 1, 2>};
+  PairKernelFn fns[10] = {pair_kernel_for(64, 4, 1),         pair_kernel_for(64, 4, 2),
+                          pair_kernel_for(128, 2, 1, false), pair_kernel_for(128, 1, 1, false),
+                          pair_kernel_for(128, 2, 2, false), pair_kernel_for(128, 1, 2, false),
+                          pair_kernel_for(128, 2, 1, true),  pair_kernel_for(128, 1, 1, true),
+                          pair_kernel_for(128, 2, 2, true),  pair_kernel_for(128, 1, 2, true)};
   for (PairKernelFn f : fns) {
     cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return fail((int)e, std::string("cudaFuncSetAttribute(pair): ") + cudaGetErrorString(e));
@@ -136,8 +158,8 @@ inline int launch_pair(const PairPlan& plan, cudaStream_t st) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, pair_kernel_for(plan.rowb, plan.mt, plan.cg), plan.tm, plan.tm_w1, plan.tm_w2,
-                                     plan.p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, pair_kernel_for(plan.rowb, plan.mt, plan.cg, plan.staged), plan.tm, plan.tm_w1, plan.tm_w2,
+                                     plan.tm_out, plan.tm_out2, plan.p);
   if (e != cudaSuccess) return fail((int)e, std::string("pair_tc launch: ") + cudaGetErrorString(e));
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("pair_tc launch: ") + cudaGetErrorString(e));

@@ -54,14 +54,14 @@ struct PairParams {
   const float* bias2;
   const __nv_bfloat16* res_act;  // == the kernel's input tensor (bf16 leaky_relu(x)), read for the residual
   const __nv_bfloat16* sum_a;    // bf16 running sum over the stage's resblocks (generator.py:44-47) or nullptr
-  float* out_f32;
-  __nv_bfloat16* out_act;
+  __nv_bfloat16* out_act;        // bf16 leaky_relu(result, slope), written through tm_out / tm_out2 (TMA stores)
 };
 
-template <int ROWB, int MT, int CG>
+template <int ROWB, int MT, int CG, bool STAGED>
 __global__ void __launch_bounds__(kConvThreads, 1)
 pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w1,
-               const __grid_constant__ CUtensorMap tm_w2, const PairParams p) {
+               const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_out,
+               const __grid_constant__ CUtensorMap tm_out2, const PairParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -70,6 +70,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   constexpr uint32_t DESC_HI = ((8u * ROWB) >> 4) | (1u << 14) | ((ROWB == 128 ? 2u : 4u) << 29);
   constexpr uint32_t SWZ = ROWB == 128 ? 7u : 3u;
   constexpr int CH_PANEL = ROWB / 2;
+  // STAGED: the c2 epilogue stages its result in shared memory and a TMA store writes it out (pair_host.cuh picks
+  // it for the epilogue-bound pairs: C >= 64 and k = 3; measured per launch in the full forward, direct -> staged:
+  // C = 128 k = 3 125 -> 111 us, C = 64 k = 3 106 -> 100 us, but C = 128 k = 11 244 -> 259 us, C = 64 k = 7 126 -> 131 us,
+  // C = 32 k = 11 136 -> 148 us: where the MMAs already saturate shared memory the extra staging traffic loses).
+  constexpr bool kStaged = STAGED;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -95,7 +100,9 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   uint64_t* acc_full = w_empty + kMaxStages;  // [2][2]
   uint64_t* acc_empty = acc_full + 4;         // [2][2]
   uint64_t* m_full = acc_empty + 4;           // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(m_full + 2);
+  uint64_t* stage_full = m_full + 2;          // [2] the c2 epilogue has staged a unit's result in the lane's M slab
+  uint64_t* stage_free = stage_full + 2;      // [2] ... and the store warp's TMA store has read it out again
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 2);
   float* s_bias1 = reinterpret_cast<float*>(bars + 64);  // [nt] biases of c1 / c2, staged once (512 B past `bars`)
   float* s_bias2 = s_bias1 + 128;
 
@@ -128,6 +135,10 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     }
     mbar_init(&m_full[0], kEpiWarps * CG);
     mbar_init(&m_full[1], kEpiWarps * CG);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&stage_full[i], kEpiWarps);   // local: every CTA stores its own units
+      mbar_init(&stage_free[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 3) {
@@ -314,6 +325,37 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       if (n >= 1) job(n - 1, 1);
     }
     if (leader) E2E_TR(4);
+  } else if (warp == 3) {
+    if (kStaged && lane == 0) {
+      // ---------------- store warp: the staged result tiles go to global memory as TMA bulk-tensor stores -------
+      // The c2 epilogue leaves a unit's bf16 result in the lane's M slab (dead between c2's last MMA and the next
+      // c1 epilogue of the lane), in the slab's own swizzled panel layout, which is what a SWIZZLE_128B / _64B
+      // tensor map reads.  One store per 64-channel panel moves the unit's r_out rows (rows past the utterance end
+      // are clipped by the TMA unit).  No LSU wavefronts, no 32-byte-per-lane global stores.
+      griddep_wait();
+      tma_prefetch_desc(&tm_out);
+      UnitIter uit;
+      uit.init(u_first, u_step, 1, p.tiles_per_b);
+      const int rows1 = p.r_out < 256 ? p.r_out : 256;
+      for (int n = 0; n < N; ++n, uit.next()) {
+        const int ln = n & 1;
+        const uint32_t par = (n >> 1) & 1;
+        mbar_wait(&stage_full[ln], par, 0x800 + ln);
+        if (uit.b < p.B) {
+          const int t0 = uit.tile * p.r_out;
+          const uint8_t* src = m_slab + ln * m_lane_bytes;
+          for (int pn = 0; pn < p.panels; ++pn) {
+            tma_store_3d(&tm_out, src + pn * m_panel_bytes, pn * CH_PANEL, t0, uit.b);
+            if (p.r_out > 256)
+              tma_store_3d(&tm_out2, src + pn * m_panel_bytes + rows1 * ROWB, pn * CH_PANEL, t0 + rows1, uit.b);
+          }
+          bulk_commit_group();
+          bulk_wait_group_read<0>();
+        }
+        mbar_arrive(&stage_free[ln]);
+      }
+      bulk_wait_group<0>();
+    }
   } else if (warp >= 4) {
     // ---------------- epilogue ----------------
     griddep_wait();  // residual / running-sum reads and every output store follow the previous kernel
@@ -329,7 +371,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
     EpiOut eo;
     eo.sum_a = p.sum_a;
-    eo.out_f32 = p.out_f32;
+    eo.out_f32 = nullptr;  // (this kernel writes bf16 activations only)
     eo.out_act = p.out_act;
     eo.slope = p.slope;
     eo.scale = p.divisor != 0.f ? 1.0f / p.divisor : 0.f;
@@ -380,6 +422,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       const unsigned long long te0 = gtime_ns();
 #endif
       mbar_wait(&acc_full[ln * 2 + 0], par, 0x600 + ln * 2);
+      if (kStaged) mbar_wait(&stage_free[ln], par ^ 1, 0x680 + ln);   // the result staged in this slab has been stored
       tc_fence_after_sync();
       E2E_TR2(2);
 #ifdef E2E_TRACE
@@ -444,40 +487,66 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       }
     };
 
-    // c2 epilogue: acc + bias2 + residual (+ running sum, * 1/divisor) -> global
+    // c2 epilogue: acc + bias2 + residual (+ running sum, * 1/divisor) -> leaky_relu -> bf16, staged in the lane's M
+    // slab at this thread's (row, columns) position in the slab's swizzled layout; the store warp moves the tile to
+    // global memory with a TMA store.  (A thread's own global stores would be 32 bytes per lane at a row pitch of
+    // 2*C bytes: ~64 L1 wavefronts per warp access, on the data pipe the tensor core's operand reads need.)
+    auto own_off = [&](int m, int cc) -> uint32_t {
+      const int n0 = cc * 16;
+      uint32_t off = static_cast<uint32_t>(m * 128 + row_in_tile) * ROWB + ((n0 % CH_PANEL) / 8) * 16;
+      off ^= ((off >> 7) & SWZ) << 4;
+      return off + (n0 / CH_PANEL) * m_panel_bytes;
+    };
+    const uint32_t soA = smem_u32(m_slab) + own_off(mA, ccA), soB = smem_u32(m_slab) + own_off(mB, ccB);
     auto epi2 = [&](int n) {
       const int ln = n & 1;
       const uint32_t par = (n >> 1) & 1;
+      const uint32_t lane_off = ln * m_lane_bytes;
 #ifdef E2E_TRACE
       const unsigned long long tf0 = gtime_ns();
 #endif
-      mbar_wait(&acc_full[ln * 2 + 1], par, 0x700 + ln * 2);
+      mbar_wait(&acc_full[ln * 2 + 1], par, 0x700 + ln * 2);   // c2's MMAs are done: accumulator ready, M slab dead
       tc_fence_after_sync();
       E2E_TR2(8);
 #ifdef E2E_TRACE
       const unsigned long long tf1 = gtime_ns();
 #endif
       const uint32_t d_tmem = tmem_base + (ln * 2 + 1) * acc_cols + lane_sel;
-      uint32_t vA[16], vB[16];
+      uint32_t vA[16], vB[16], pk[8];
       float4 bv[4];
       tmem_ld_32x16(d_tmem + mA * p.nt + ccA * 16, vA);
       lds_bias(s_bias2, ccA, bv);
       tmem_ld_wait();
       E2E_TR2(9);
       tmem_ld_32x16(d_tmem + mB * p.nt + ccB * 16, vB);
-      epi_finish16(vA, bv, rqa, sqa, eo, offa, va);
+      if (kStaged) {
+        epi_compute16(vA, bv, rqa, sqa, eo, pk);
+        st_shared_u4(soA + lane_off, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        st_shared_u4((soA + lane_off) ^ 16u, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+      } else {
+        epi_finish16(vA, bv, rqa, sqa, eo, offa, va);
+      }
       E2E_TR2(10);
       lds_bias(s_bias2, ccB, bv);
       tmem_ld_wait();
       E2E_TR2(11);
-      // every TMEM read of this warp has completed: release the accumulator before the global stores of item B
+      // every TMEM read of this warp has completed: release the accumulator
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
         if (CG == 2) mbar_arrive_remote(&acc_empty[ln * 2 + 1], 0);
         else mbar_arrive(&acc_empty[ln * 2 + 1]);
       }
-      epi_finish16(vB, bv, rqb, sqb, eo, offb, vb);
+      if (kStaged) {
+        epi_compute16(vB, bv, rqb, sqb, eo, pk);
+        st_shared_u4(soB + lane_off, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        st_shared_u4((soB + lane_off) ^ 16u, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+        fence_proxy_async_smem();   // the staged tile is read by the TMA unit (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stage_full[ln]);
+      } else {
+        epi_finish16(vB, bv, rqb, sqb, eo, offb, vb);
+      }
       E2E_TR2(12);
 #ifdef E2E_TRACE
       if (threadIdx.x == 128 && blockIdx.x < 512) {

@@ -397,8 +397,10 @@ static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B,
   p.res_act = in;
   p.res_inv_slope = 10.0f;
   p.sum_a = sum_a;
-  p.out_f32 = out_f32;
+  if (out_f32 || !out_act) return fail(-2, "fused pair: bf16 activation output only");
   p.out_act = out_act;
+  rc = pair_output_maps(op.pair, out_act, B, T, L1.cin);
+  if (rc) return rc;
   p.slope_mid = 0.1f;
   p.slope = slope;
   p.divisor = divisor;

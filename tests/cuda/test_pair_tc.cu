@@ -32,11 +32,11 @@ struct Cfg {
 static const Cfg kCfgs[] = {
     {"c128 k3 d1 small", 128, 3, 1, 2, 300, 0, 0, 0, 1},
     {"c128 k11 d5", 128, 11, 5, 3, 1000, 0, 0, 0, 1},
-    {"c128 k7 d3 sum->f32", 128, 7, 3, 2, 777, 1, 0, 1, 0},
+    {"c128 k7 d3 sum", 128, 7, 3, 2, 777, 1, 0, 0, 1},
     {"c64 k11 d5", 64, 11, 5, 2, 1500, 0, 0, 0, 1},
     {"c64 k3 d1 sum div3", 64, 3, 1, 2, 1501, 1, 1, 0, 1},
     {"c32 k11 d3", 32, 11, 3, 2, 2000, 0, 0, 0, 1},
-    {"c32 k7 d5 f32 only", 32, 7, 5, 2, 3000, 0, 0, 1, 0},
+    {"c32 k7 d5", 32, 7, 5, 2, 3000, 0, 0, 0, 1},
     {"c128 k3 d1 T=1", 128, 3, 1, 2, 1, 0, 0, 0, 1},
     {"c32 k11 d5 T=100", 32, 11, 5, 3, 100, 0, 0, 0, 1},
     // performance shapes (B=16, 5 s)
@@ -187,13 +187,17 @@ int main(int argc, char** argv) {
   p.res_act = dx;
   p.res_inv_slope = 10.0f;
   p.sum_a = dsum;
-  p.out_f32 = dout;
   p.out_act = dact;
+  rc = pair_output_maps(plan, dact, c.B, c.T, c.C);
+  if (rc) {
+    printf("output tensor maps failed: %s\n", last_error().c_str());
+    return 3;
+  }
   p.slope_mid = 0.1f;
   p.slope = 0.1f;
   p.divisor = c.div3 ? 3.0f : 0.f;
-  printf("  plan: cg=%d grid=%d units=%d smem=%d mt=%d a_rows=%d box=%d m_rows=%d r_out=%d stages=%d stage_bytes=%d chunks=%d\n",
-         plan.cg, plan.grid.x, p.n_units, plan.smem_bytes, plan.mt, p.a_rows, p.box_rows, p.m_rows, p.r_out, p.n_stages,
+  printf("  plan: cg=%d staged=%d grid=%d units=%d smem=%d mt=%d a_rows=%d box=%d m_rows=%d r_out=%d stages=%d stage_bytes=%d chunks=%d\n",
+         plan.cg, (int)plan.staged, plan.grid.x, p.n_units, plan.smem_bytes, plan.mt, p.a_rows, p.box_rows, p.m_rows, p.r_out, p.n_stages,
          p.stage_bytes, p.n_chunks);
   rc = launch_pair(plan, 0);
   if (rc) {
