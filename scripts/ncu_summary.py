@@ -24,6 +24,10 @@ want = [
     "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "smsp__sass_inst_executed_op_tmem_ldt.sum",
+    # the L1 data pipe is shared by the LSU (global / shared accesses of the threads) and the tensor core's operand reads
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
 ]
 print("== %s" % rep.split("/")[-1])
 for k in want:
