@@ -65,6 +65,8 @@ struct ConvParams {
   float divisor;        // epilogue: 0 = none, else out /= divisor (generator.py:48, xs / num_kernels)
   float slope;          // LeakyReLU slope applied to out_act
   int act_tanh;         // 1: out_act = tanh(result) instead (Postnet)
+  int sum_tiled;        // sum_a is in the tiled8 layout (epilogue.cuh)
+  int out_tiled;        // out_act is written in the tiled8 layout
   int8_t shift[kMaxNTiles][kMaxTaps];  // row shift of each tap, per N tile
   const uint8_t* w;     // packed weights
   const float* bias;    // [n_total]
@@ -381,6 +383,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         n0 = nti * p.nt + cc * 16;
         return (static_cast<size_t>(b) * p.T + (valid ? t : 0)) * p.n_total + n0;
       };
+      const int t8 = (p.T + 7) >> 3, c16 = p.n_total >> 4;
+      auto tiled_off = [&](int item, int n0) -> size_t {
+        const int m = item / nchunk;
+        return tiled8_off(b, t0 + m * 128 + row_in_tile, n0 >> 4, t8, c16);
+      };
       auto prefetch = [&](int item, uint4 (&rq)[2], uint4 (&sa)[2]) {
         int n0;
         bool valid;
@@ -388,7 +395,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         rq[0] = rq[1] = make_uint4(0u, 0u, 0u, 0u);
         if (valid) {
           if (p.res_act) ld_global_256(p.res_act + off, rq[0], rq[1]);  // plain loads: may be updated in place
-          if (p.sum_a) ld_global_256(p.sum_a + off, sa[0], sa[1]);
+          if (p.sum_a) ld_global_256(p.sum_a + (p.sum_tiled ? tiled_off(item, n0) : off), sa[0], sa[1]);
         }
       };
       prefetch(part, rqa, saa);  // overlaps the MMAs of this unit
@@ -408,7 +415,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
         tmem_ld_wait();
-        epi_finish16(v, bv, rq, sa, eo, off, valid);
+        epi_finish16(v, bv, rq, sa, eo, (p.out_tiled && valid) ? tiled_off(item, n0) : off, valid);
         prefetch(item + 8, rq, sa);  // refill this slot for the item after next
       };
       for (int item = part; item < items; item += 8) {

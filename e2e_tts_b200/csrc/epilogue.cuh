@@ -59,6 +59,13 @@ struct UnitIter {
   }
 };
 
+// Tiled layout of the running-sum tensors S0 / S1 (touched only by epilogues, never by TMA): [B][ceil(T/8)][C/16][8][16].
+// A warp's natural access - 32 consecutive rows x 16 channels, 32 bytes per lane - is then four contiguous 256-byte
+// blocks (8 lines) instead of 32 bytes at a row pitch of 2*C bytes (32 lines, ~64 L1 wavefronts per warp access).
+__device__ __forceinline__ size_t tiled8_off(int b, int t, int chunk16, int t8, int c16) {
+  return ((static_cast<size_t>(b) * t8 + (t >> 3)) * c16 + chunk16) * 128 + (t & 7) * 16;
+}
+
 struct EpiOut {
   const __nv_bfloat16* sum_a;  // bf16 running resblock sum to add (nullptr = absent)
   float* out_f32;

@@ -54,6 +54,8 @@ struct PairParams {
   const float* bias2;
   const __nv_bfloat16* res_act;  // == the kernel's input tensor (bf16 leaky_relu(x)), read for the residual
   const __nv_bfloat16* sum_a;    // bf16 running sum over the stage's resblocks (generator.py:44-47) or nullptr
+  int sum_tiled;                 // sum_a is in the tiled8 layout (epilogue.cuh)
+  int out_tiled;                 // out_act is written in the tiled8 layout (direct stores; never with STAGED)
   __nv_bfloat16* out_act;        // bf16 leaky_relu(result, slope), written through tm_out / tm_out2 (TMA stores)
 };
 
@@ -477,13 +479,20 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       offa = (static_cast<size_t>(b) * p.T + (va ? t0 + oa : 0)) * p.nt + ccA * 16;
       offb = (static_cast<size_t>(b) * p.T + (vb ? t0 + ob : 0)) * p.nt + ccB * 16;
       rqa[0] = rqa[1] = rqb[0] = rqb[1] = make_uint4(0u, 0u, 0u, 0u);
+      const int t8 = (p.T + 7) >> 3, c16 = p.nt >> 4;
+      const size_t ta = (p.sum_tiled | p.out_tiled) && va ? tiled8_off(b, t0 + oa, ccA, t8, c16) : 0;
+      const size_t tb = (p.sum_tiled | p.out_tiled) && vb ? tiled8_off(b, t0 + ob, ccB, t8, c16) : 0;
       if (va) {
         ld_global_256(p.res_act + offa, rqa[0], rqa[1]);
-        if (p.sum_a) ld_global_256(p.sum_a + offa, sqa[0], sqa[1]);
+        if (p.sum_a) ld_global_256(p.sum_a + (p.sum_tiled ? ta : offa), sqa[0], sqa[1]);
       }
       if (vb) {
         ld_global_256(p.res_act + offb, rqb[0], rqb[1]);
-        if (p.sum_a) ld_global_256(p.sum_a + offb, sqb[0], sqb[1]);
+        if (p.sum_a) ld_global_256(p.sum_a + (p.sum_tiled ? tb : offb), sqb[0], sqb[1]);
+      }
+      if (p.out_tiled) {   // from here on offa / offb address the output
+        offa = ta;
+        offb = tb;
       }
     };
 

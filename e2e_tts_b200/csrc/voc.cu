@@ -66,6 +66,8 @@ struct e2e_voc {
   int n_sms = 148;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // one-shot profiling events
   int last_launches = 0;
+  bool tiled_sums = true;                            // S0 / S1 in the tiled8 layout (E2E_NO_TILED_SUMS=1: natural)
+  const __nv_bfloat16 *cur_s0 = nullptr, *cur_s1 = nullptr;  // the S buffers of the plan being built
 };
 
 static int pick_nt(int cout) { return cout >= 256 ? 256 : cout; }
@@ -311,7 +313,8 @@ static void carve(const e2e_voc* v, int B, int T, void* ws, Buffers& b) {
     return r;
   };
   // + one row per utterance: the iSTFTNet head reflection-pads the last stage's tensor (generator.py:102)
-  const size_t E = stage_elems(v, B, T) + (size_t)B * v->cfg.upsample_initial_channel;
+  // and 7 rows: the running-sum tensors S0 / S1 are tiled in 8-row blocks (epilogue.cuh)
+  const size_t E = stage_elems(v, B, T) + (size_t)B * 8 * v->cfg.upsample_initial_channel;
   b.melA = (__nv_bfloat16*)take((size_t)B * T * v->cin_pad * 2);
   b.preA = (__nv_bfloat16*)take((size_t)B * T * v->cfg.upsample_initial_channel * 2);
   b.A0 = (__nv_bfloat16*)take(E * 2);
@@ -371,6 +374,8 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
   p.out_act = out_act;
   p.slope = slope;
   p.divisor = divisor;
+  p.sum_tiled = sum_a != nullptr && v->tiled_sums;         // S0 / S1 are only ever read as sum_a ...
+  p.out_tiled = out_act != nullptr && v->tiled_sums && (out_act == v->cur_s0 || out_act == v->cur_s1);  // ... and written here
   ops.push_back(op);
   return 0;
 }
@@ -399,6 +404,9 @@ static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B,
   p.sum_a = sum_a;
   if (out_f32 || !out_act) return fail(-2, "fused pair: bf16 activation output only");
   p.out_act = out_act;
+  p.sum_tiled = sum_a != nullptr && v->tiled_sums;
+  p.out_tiled = v->tiled_sums && (out_act == v->cur_s0 || out_act == v->cur_s1);
+  if (p.out_tiled) op.pair.staged = false;   // the TMA store writes the natural layout
   rc = pair_output_maps(op.pair, out_act, B, T, L1.cin);
   if (rc) return rc;
   p.slope_mid = 0.1f;
@@ -411,6 +419,9 @@ static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B,
 static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) {
   Buffers bf;
   carve(v, B, T, ws, bf);
+  v->tiled_sums = std::getenv("E2E_NO_TILED_SUMS") == nullptr;
+  v->cur_s0 = bf.S0;
+  v->cur_s1 = bf.S1;
   const e2e_voc_config& c = v->cfg;
   const float kSlope = 0.1f;  // LRELU_SLOPE, generator.py:10 / layers.py:7
   {
