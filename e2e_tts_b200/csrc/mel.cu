@@ -209,14 +209,15 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
 #pragma unroll
     for (int c = 1; c < 8; ++c) S2[hi * 72 + c * 9 + lo] = cmul(a[c], t2[c]);
     group_sync(g);
-    // pass 3: thread (k1 = hi, c = lo) reads U[k1][c][b]; result Z[k1 + 8 c + 64 d] -> S3 (aliases S1)
+    // pass 3: thread (k1 = hi, c = lo) reads U[k1][c][b]; result Z[k] , k = k1 + 8 c + 64 d, -> S3[k ^ ((k >> 3) & 7)] (aliases S1;
+    // the xor spreads both this scattered store and the recombination's paired loads over the banks)
 #pragma unroll
     for (int q = 0; q < 8; ++q) a[q] = S2[hi * 72 + lo * 9 + q];
     dft8(a);
 #pragma unroll
     for (int d = 0; d < 8; ++d) {
       const int k = hi + 8 * lo + 64 * d;
-      S1[k + (k >> 3)] = a[d];
+      S1[k ^ ((k >> 3) & 7)] = a[d];
     }
     group_sync(g);
     // real-FFT recombination: thread t owns the bin pairs (k, 512 - k), k = t + 64 j, j = 0..3; thread 0 also
@@ -227,8 +228,8 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
     for (int j = 0; j < 4; ++j) {
       const int k = t + 64 * j;
       const int kk = (512 - k) & 511;
-      const float2 za = S1[k + (k >> 3)];
-      const float2 zb = S1[kk + (kk >> 3)];
+      const float2 za = S1[k ^ ((k >> 3) & 7)];
+      const float2 zb = S1[kk ^ ((kk >> 3) & 7)];
       const float2 ze = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
       const float2 zo = make_float2(0.5f * (za.y + zb.y), -0.5f * (za.x - zb.x));
       const float2 wz = cmul(tw_s[k], zo);
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
       }
     }
     if (t == 0 && 256 < nb) {
-      const float2 z = S1[256 + 32];
+      const float2 z = S1[256];  // 256 ^ ((256 >> 3) & 7)
       mag[256 + (256 / BPT) * (PITCH - BPT)] = sqrt_approx(z.x * z.x + z.y * z.y + 1e-9f);
     }
     // energy^2 = sum_{k=0..512} (|X_k|^2 + 1e-9) = (1024 sum xw^2 + X_0^2 + X_512^2) / 2 + 513e-9   (stft.py:84)

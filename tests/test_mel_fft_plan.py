@@ -45,18 +45,18 @@ def kernel_fft1024_real(xw):
         v = dft8([S2[k1 * 72 + c * 9 + b] for b in range(8)])
         for d in range(8):
             k = k1 + 8 * c + 64 * d
-            S3[k + (k >> 3)] = v[d]
+            S3[k ^ ((k >> 3) & 7)] = v[d]
     X = np.zeros(513, complex)
     for t in range(64):                                # post pass: thread t, bin pairs (k, 512 - k), k = t + 64 j
         for j in range(4):
             k = t + 64 * j
             kk = (512 - k) % 512
-            a, bq = S3[k + (k >> 3)], np.conj(S3[kk + (kk >> 3)])
+            a, bq = S3[k ^ ((k >> 3) & 7)], np.conj(S3[kk ^ ((kk >> 3) & 7)])
             ze, zo = (a + bq) / 2, (a - bq) / 2j
             wz = tw[k] * zo
             X[k] = ze + wz
             X[512 - k] = np.conj(ze - wz)
-    z = S3[256 + 32]                                   # thread 0: bin 256 (only |X| is used by the kernel)
+    z = S3[256]                                        # thread 0: bin 256 (only |X| is used by the kernel)
     X[256] = np.conj(z)
     return X
 
@@ -77,7 +77,7 @@ def test_fft_choreography_matches_rfft():
 def test_smem_maps_are_injective():
     s1 = {k1 * 72 + n2 for k1 in range(8) for n2 in range(64)}
     s2 = {k1 * 72 + c * 9 + b for k1 in range(8) for c in range(8) for b in range(8)}
-    s3 = {k + (k >> 3) for k in range(512)}
+    s3 = {k ^ ((k >> 3) & 7) for k in range(512)}
     assert len(s1) == 512 and len(s2) == 512 and len(s3) == 512
     assert max(s1) < 576 and max(s2) < 576 and max(s3) < 576
 
