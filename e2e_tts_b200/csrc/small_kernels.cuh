@@ -58,17 +58,23 @@ constexpr int kPostTile = 512;  // output samples per block (2 per thread)
 // w: [k][C] fp32 (tap-major), one output channel.  A block stages the bf16 rows [t0 - half, t0 + 512 + half) in
 // shared memory with coalesced 16-byte loads (rows outside the utterance = 0: conv_post's zero padding) and every
 // thread produces two adjacent samples, so each staged row is unpacked once for two outputs.
+// The K*C weights arrive as a kernel parameter (constant bank): every thread of a warp reads the same weight at the
+// same time, which the constant cache broadcasts without touching the shared-memory pipe the staged rows need.
+template <int N>
+struct PostWeights {
+  float w[N];
+};
+
 template <int C, int K>
 __global__ void __launch_bounds__(256)
-post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, float bias, int B, int T,
-                      const PostOut out) {
+post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const __grid_constant__ PostWeights<K * C> pw, float bias,
+                      int B, int T, const PostOut out) {
   constexpr int HALF = (K - 1) / 2;
   constexpr int ROWS = kPostTile + 2 * HALF;
   constexpr int ROW16 = C / 8;       // uint4 per row
   constexpr int PITCH = ROW16 + 1;   // padded row pitch: adjacent threads read rows two apart -> 2-way conflicts at most
-  __shared__ float sw[K * C];
   __shared__ uint4 rows[ROWS * PITCH];
-  for (int i = threadIdx.x; i < K * C; i += blockDim.x) sw[i] = w[i];
+  const float* sw = pw.w;
   const int t0 = blockIdx.x * kPostTile;
   const int b = blockIdx.y;
   const uint4* src = reinterpret_cast<const uint4*>(act + (long long)b * T * C);

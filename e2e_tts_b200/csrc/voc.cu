@@ -66,6 +66,7 @@ struct e2e_voc {
   int n_sms = 148;
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // one-shot profiling events
   int last_launches = 0;
+  PostWeights<7 * 32> post_w{};                      // conv_post weights [k][C] for the 32-channel, k = 7 kernel
   bool tiled_sums = true;                            // S0 / S1 in the tiled8 layout (E2E_NO_TILED_SUMS=1: natural)
   const __nv_bfloat16 *cur_s0 = nullptr, *cur_s1 = nullptr;  // the S buffers of the plan being built
 };
@@ -246,6 +247,7 @@ extern "C" int e2e_voc_load_layer(e2e_voc* v, const char* name, const float* wei
     if ((e = cudaMemcpy(L.d_w, w.data(), w.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
       return fail((int)e, "cudaMemcpy");
     L.post_bias = bias[0];
+    if (w.size() == sizeof(v->post_w.w) / sizeof(float)) memcpy(v->post_w.w, w.data(), sizeof(v->post_w.w));
     L.loaded = true;
     v->plans.clear();
     return 0;
@@ -605,8 +607,7 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
       const int Tout = T * v->hop;
       if (L.cin == 32 && L.k == 7) {
         dim3 grid((Tout + kPostTile - 1) / kPostTile, B);
-        post_conv_tanh_kernel<32, 7><<<grid, 256, 0, st>>>(bf.Y, reinterpret_cast<const float*>(L.d_w), L.post_bias, B,
-                                                           Tout, post);
+        post_conv_tanh_kernel<32, 7><<<grid, 256, 0, st>>>(bf.Y, v->post_w, L.post_bias, B, Tout, post);
       } else {
         dim3 grid((Tout + 255) / 256, B);
         post_conv_tanh_generic_kernel<<<grid, 256, 0, st>>>(bf.Y, reinterpret_cast<const float*>(L.d_w), L.post_bias,
