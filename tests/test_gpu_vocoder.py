@@ -185,3 +185,43 @@ def test_host_pipeline_matches_direct_calls():
     with torch.no_grad():
         for m, o in zip(mels[:3], pcm):
             assert torch.equal(o, voc.forward_pcm16(m.cuda()).cpu())
+
+
+ALT_CONFIGS = {
+    # four x4 stages (hop 256), ResBlock1
+    "x4x4x4x4": {"resblock": 1, "upsample_rates": [4, 4, 4, 4], "upsample_kernel_sizes": [8, 8, 8, 8],
+                 "upsample_initial_channel": 512, "resblock_kernel_sizes": [3, 7, 11],
+                 "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]]},
+    # HiFi-GAN V3-like: three stages, ResBlock2, other kernel sizes / dilations
+    "v3like": {"resblock": 2, "upsample_rates": [8, 8, 4], "upsample_kernel_sizes": [16, 16, 8],
+               "upsample_initial_channel": 256, "resblock_kernel_sizes": [3, 5, 7],
+               "resblock_dilation_sizes": [[1, 2], [2, 6], [3, 12]]},
+    # two kernels per stage, wide dilations
+    "two_kernels": {"resblock": 1, "upsample_rates": [8, 8, 2, 2], "upsample_kernel_sizes": [16, 16, 4, 4],
+                    "upsample_initial_channel": 512, "resblock_kernel_sizes": [5, 9],
+                    "resblock_dilation_sizes": [[1, 2, 4], [1, 4, 9]]},
+}
+
+
+@pytest.mark.parametrize("name", sorted(ALT_CONFIGS))
+def test_other_generator_configs_against_oracle(name):
+    """The C ABI takes any `hifigan:` mapping within its stated limits (channel counts of 32 or multiples of 64,
+    kernel = 2 x stride): other stage counts, kernel sizes, dilations and ResBlock2 against the oracle."""
+    cfg = ALT_CONFIGS[name]
+    voc, sd = build(cfg, 60, "strong")
+    hop = int(np.prod(cfg["upsample_rates"]))
+    mel = mel_like(2, 37, 61)
+    with torch.no_grad():
+        got = voc(mel.cuda())
+        want = ho.hifigan_forward(sd, cfg, mel)
+    assert got.shape == (2, 1, hop * 37)
+    check(got, want, name)
+
+
+def test_unsupported_config_is_refused_cleanly():
+    cfg = dict(ho.DEFAULT_CONFIG, upsample_initial_channel=256)     # last stage would have 16 channels
+    voc, _ = build(cfg, 61, "strong")
+    with pytest.raises(Exception) as ei:
+        with torch.no_grad():
+            voc(mel_like(1, 8, 1).cuda())
+    assert "channel" in str(ei.value)
