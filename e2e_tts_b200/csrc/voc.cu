@@ -67,8 +67,6 @@ struct e2e_voc {
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // one-shot profiling events
   int last_launches = 0;
   PostWeights<7 * 32> post_w{};                      // conv_post weights [k][C] for the 32-channel, k = 7 kernel
-  bool tiled_sums = true;                            // S0 / S1 in the tiled8 layout (E2E_NO_TILED_SUMS=1: natural)
-  const __nv_bfloat16 *cur_s0 = nullptr, *cur_s1 = nullptr;  // the S buffers of the plan being built
 };
 
 static int pick_nt(int cout) { return cout >= 256 ? 256 : cout; }
@@ -336,9 +334,11 @@ extern "C" size_t e2e_voc_workspace_bytes(const e2e_voc* v, int32_t B, int32_t T
 }
 
 // One conv launch: input activation `in` ([B][T][cin] bf16), outputs as requested.
+enum : int { kSumTiled = 1, kOutTiled = 2 };  // which epilogue-only tensors of an op are in the tiled8 layout
+
 static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int T, const __nv_bfloat16* in,
                         const __nv_bfloat16* res_act, const __nv_bfloat16* sum_a, float* out_f32, __nv_bfloat16* out_act,
-                        float slope, float divisor) {
+                        float slope, float divisor, int tiled = 0) {
   Layer& L = v->layers[layer];
   Op op;
   op.kind = 1;
@@ -376,15 +376,16 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
   p.out_act = out_act;
   p.slope = slope;
   p.divisor = divisor;
-  p.sum_tiled = sum_a != nullptr && v->tiled_sums;         // S0 / S1 are only ever read as sum_a ...
-  p.out_tiled = out_act != nullptr && v->tiled_sums && (out_act == v->cur_s0 || out_act == v->cur_s1);  // ... and written here
+  p.sum_tiled = sum_a != nullptr && (tiled & kSumTiled);
+  p.out_tiled = out_act != nullptr && (tiled & kOutTiled);
   ops.push_back(op);
   return 0;
 }
 
 // One fused launch for  x + c2(lrelu(c1(lrelu(x))))  (pair_tc.cuh).  `in` holds bf16 leaky_relu(x, 0.1).
 static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B, int T, const __nv_bfloat16* in,
-                        const __nv_bfloat16* sum_a, float* out_f32, __nv_bfloat16* out_act, float slope, float divisor) {
+                        const __nv_bfloat16* sum_a, float* out_f32, __nv_bfloat16* out_act, float slope, float divisor,
+                        int tiled = 0) {
   const Layer& L1 = v->layers[l1];
   const Layer& L2 = v->layers[l2];
   Op op;
@@ -406,8 +407,8 @@ static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B,
   p.sum_a = sum_a;
   if (out_f32 || !out_act) return fail(-2, "fused pair: bf16 activation output only");
   p.out_act = out_act;
-  p.sum_tiled = sum_a != nullptr && v->tiled_sums;
-  p.out_tiled = v->tiled_sums && (out_act == v->cur_s0 || out_act == v->cur_s1);
+  p.sum_tiled = sum_a != nullptr && (tiled & kSumTiled);
+  p.out_tiled = (tiled & kOutTiled) != 0;
   if (p.out_tiled) op.pair.staged = false;   // the TMA store writes the natural layout
   rc = pair_output_maps(op.pair, out_act, B, T, L1.cin);
   if (rc) return rc;
@@ -421,9 +422,9 @@ static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B,
 static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) {
   Buffers bf;
   carve(v, B, T, ws, bf);
-  v->tiled_sums = std::getenv("E2E_NO_TILED_SUMS") == nullptr;
-  v->cur_s0 = bf.S0;
-  v->cur_s1 = bf.S1;
+  // S0 / S1 (the running resblock sums) are written and read by epilogues only, so they live in the tiled8
+  // layout (epilogue.cuh tiled8_off); E2E_NO_TILED_SUMS=1 keeps them in the natural one (A/B switch).
+  const bool tiled_sums = std::getenv("E2E_NO_TILED_SUMS") == nullptr;
   const e2e_voc_config& c = v->cfg;
   const float kSlope = 0.1f;  // LRELU_SLOPE, generator.py:10 / layers.py:7
   {
@@ -464,12 +465,14 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
         __nv_bfloat16* oact = fused ? ((m & 1) ? bf.M : bf.A1) : bf.A1;
         const __nv_bfloat16* sum_in = nullptr;
         float divisor = 0.f, slope = kSlope;
+        int tiled = 0;
         if (last) {
           // xs += resblock_j(x) (generator.py:44-47): the running sum is kept in bf16 (slope 1 = no activation),
           // alternating between S0 and S1 so no launch reads and writes the same buffer
           oact = (j & 1) ? bf.S1 : bf.S0;
           slope = 1.0f;
           sum_in = j > 0 ? ((j & 1) ? bf.S0 : bf.S1) : nullptr;
+          if (tiled_sums) tiled = kSumTiled | (j + 1 == c.num_kernels ? 0 : kOutTiled);
           if (j + 1 == c.num_kernels) {           // x = xs / num_kernels   (generator.py:48)
             oact = bf.Y;
             divisor = (float)c.num_kernels;
@@ -479,7 +482,7 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
         if (fused) {
           rc = make_pair_op(v, ops, v->by_name[base + ".convs1." + std::to_string(m)],
                             v->by_name[base + ".convs2." + std::to_string(m)], B, Ts, ain, sum_in, of32, oact, slope,
-                            divisor);
+                            divisor, tiled);
           if (rc) return rc;
           ain = oact;
         } else if (c.resblock == 1) {
@@ -487,12 +490,12 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
                             nullptr, bf.M, kSlope, 0.f);
           if (rc) return rc;
           rc = make_conv_op(v, ops, v->by_name[base + ".convs2." + std::to_string(m)], B, Ts, bf.M, ain, sum_in,
-                            of32, oact, slope, divisor);
+                            of32, oact, slope, divisor, tiled);
           if (rc) return rc;
           ain = bf.A1;
         } else {
           rc = make_conv_op(v, ops, v->by_name[base + ".convs." + std::to_string(m)], B, Ts, ain, ain, sum_in, of32,
-                            oact, slope, divisor);
+                            oact, slope, divisor, tiled);
           if (rc) return rc;
           ain = bf.A1;
         }
