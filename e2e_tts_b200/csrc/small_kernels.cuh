@@ -53,11 +53,17 @@ __device__ __forceinline__ int16_t to_pcm16(float y, float scale) {
 }
 
 constexpr int kPostMaxW = 7 * 64;
-constexpr int kPostTile = 512;  // output samples per block (2 per thread)
+constexpr int kPostThreads = 96;
+constexpr int kPostOpt = 5;  // output samples per thread (measured, 16 x 5 s: 2 -> 55 us, 3 -> 54 us, 5 -> 44 us, 7 -> 51 us)
+constexpr int kPostTile = kPostThreads * kPostOpt;  // output samples per block
 
-// w: [k][C] fp32 (tap-major), one output channel.  A block stages the bf16 rows [t0 - half, t0 + 512 + half) in
+// w: [k][C] fp32 (tap-major), one output channel.  A block stages the bf16 rows [t0 - half, t0 + tile + half) in
 // shared memory with coalesced 16-byte loads (rows outside the utterance = 0: conv_post's zero padding) and every
-// thread produces two adjacent samples, so each staged row is unpacked once for two outputs.
+// thread produces OPT adjacent samples, so each staged row is read and unpacked once for up to OPT outputs (OPT + K - 1
+// rows per thread instead of OPT * K).  With an odd row pitch (in 16-byte units) and an odd OPT the lanes of a quarter
+// warp start in eight different 16-byte bank groups: the 128-bit row reads are conflict-free (OPT = 2 was 2-way).
+// For every output the taps are accumulated in increasing order with the channels innermost - the result does not
+// depend on OPT.
 // The K*C weights arrive as a kernel parameter (constant bank): every thread of a warp reads the same weight at the
 // same time, which the constant cache broadcasts without touching the shared-memory pipe the staged rows need.
 template <int N>
@@ -65,31 +71,34 @@ struct PostWeights {
   float w[N];
 };
 
-template <int C, int K>
-__global__ void __launch_bounds__(256)
+template <int C, int K, int OPT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const __grid_constant__ PostWeights<K * C> pw, float bias,
                       int B, int T, const PostOut out) {
   constexpr int HALF = (K - 1) / 2;
-  constexpr int ROWS = kPostTile + 2 * HALF;
+  constexpr int TILE = OPT * THREADS;
+  constexpr int ROWS = TILE + 2 * HALF;
   constexpr int ROW16 = C / 8;       // uint4 per row
-  constexpr int PITCH = ROW16 + 1;   // padded row pitch: adjacent threads read rows two apart -> 2-way conflicts at most
+  constexpr int PITCH = ROW16 | 1;   // odd row pitch
   __shared__ uint4 rows[ROWS * PITCH];
   const float* sw = pw.w;
-  const int t0 = blockIdx.x * kPostTile;
+  const int t0 = blockIdx.x * TILE;
   const int b = blockIdx.y;
   const uint4* src = reinterpret_cast<const uint4*>(act + (long long)b * T * C);
-  for (int i = threadIdx.x; i < ROWS * ROW16; i += blockDim.x) {
+  for (int i = threadIdx.x; i < ROWS * ROW16; i += THREADS) {
     const int r = i / ROW16;
     const int t = t0 - HALF + r;
     rows[r * PITCH + (i - r * ROW16)] =
         (t >= 0 && t < T) ? __ldg(src + (long long)t * ROW16 + (i - r * ROW16)) : make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
-  const int o = 2 * threadIdx.x;  // first of this thread's two outputs, relative to t0
-  float acc0 = bias, acc1 = bias;
+  const int o = OPT * threadIdx.x;  // first of this thread's outputs, relative to t0
+  float acc[OPT];
 #pragma unroll
-  for (int j = 0; j <= K; ++j) {  // staged row o + j feeds output o with tap j and output o+1 with tap j-1
-    const uint4* row = rows + (o + j) * PITCH;
+  for (int q = 0; q < OPT; ++q) acc[q] = bias;
+#pragma unroll
+  for (int r = 0; r < K + OPT - 1; ++r) {  // staged row o + r feeds output o + q with tap r - q
+    const uint4* row = rows + (o + r) * PITCH;
 #pragma unroll
     for (int c8 = 0; c8 < ROW16; ++c8) {
       const uint4 v = row[c8];
@@ -97,13 +106,13 @@ post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const __grid_consta
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float lo = __uint_as_float(u[i] << 16), hi = __uint_as_float(u[i] & 0xffff0000u);
-        if (j < K) {
-          acc0 = fmaf(lo, sw[j * C + c8 * 8 + 2 * i], acc0);
-          acc0 = fmaf(hi, sw[j * C + c8 * 8 + 2 * i + 1], acc0);
-        }
-        if (j > 0) {
-          acc1 = fmaf(lo, sw[(j - 1) * C + c8 * 8 + 2 * i], acc1);
-          acc1 = fmaf(hi, sw[(j - 1) * C + c8 * 8 + 2 * i + 1], acc1);
+#pragma unroll
+        for (int q = 0; q < OPT; ++q) {
+          const int j = r - q;
+          if (j >= 0 && j < K) {
+            acc[q] = fmaf(lo, sw[j * C + c8 * 8 + 2 * i], acc[q]);
+            acc[q] = fmaf(hi, sw[j * C + c8 * 8 + 2 * i + 1], acc[q]);
+          }
         }
       }
     }
@@ -112,23 +121,15 @@ post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const __grid_consta
   if (out.pcm) {
     const long long valid = out.lens ? (long long)out.lens[b] * out.hop : (long long)T;
     int16_t* dst = out.pcm + (long long)b * T + t;
-    const int16_t s0 = t < valid ? to_pcm16(tanhf(acc0), out.scale) : (int16_t)0;
-    const int16_t s1 = t + 1 < valid ? to_pcm16(tanhf(acc1), out.scale) : (int16_t)0;
-    if (t + 1 < T && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
-      *reinterpret_cast<uint32_t*>(dst) = (uint32_t)(uint16_t)s0 | ((uint32_t)(uint16_t)s1 << 16);
-    } else {
-      if (t < T) dst[0] = s0;
-      if (t + 1 < T) dst[1] = s1;
-    }
+#pragma unroll
+    for (int q = 0; q < OPT; ++q)
+      if (t + q < T) dst[q] = t + q < valid ? to_pcm16(tanhf(acc[q]), out.scale) : (int16_t)0;
     return;
   }
   float* dst = out.wav + (long long)b * T + t;
-  if (t + 1 < T && (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
-    *reinterpret_cast<float2*>(dst) = make_float2(tanhf(acc0), tanhf(acc1));
-  } else {
-    if (t < T) dst[0] = tanhf(acc0);
-    if (t + 1 < T) dst[1] = tanhf(acc1);
-  }
+#pragma unroll
+  for (int q = 0; q < OPT; ++q)
+    if (t + q < T) dst[q] = tanhf(acc[q]);
 }
 
 // Generic fallback (any C multiple of 8, any odd k): one output per thread, rows read through L1.

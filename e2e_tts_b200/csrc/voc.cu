@@ -610,7 +610,8 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
       const int Tout = T * v->hop;
       if (L.cin == 32 && L.k == 7) {
         dim3 grid((Tout + kPostTile - 1) / kPostTile, B);
-        post_conv_tanh_kernel<32, 7><<<grid, 256, 0, st>>>(bf.Y, v->post_w, L.post_bias, B, Tout, post);
+        post_conv_tanh_kernel<32, 7, kPostOpt, kPostThreads>
+            <<<grid, kPostThreads, 0, st>>>(bf.Y, v->post_w, L.post_bias, B, Tout, post);
       } else {
         dim3 grid((Tout + 255) / 256, B);
         post_conv_tanh_generic_kernel<<<grid, 256, 0, st>>>(bf.Y, reinterpret_cast<const float*>(L.d_w), L.post_bias,
