@@ -81,9 +81,11 @@ struct ConvPlan {
   ConvParams p{};
   CUtensorMap tm{};
   CUtensorMap tm_w{};  // packed weight image as a [rows][rowb] matrix (CTA-pair form only)
+  CUtensorMap tm_out{};  // out_act as [B][T][n_total], box = 64 columns x 128 rows (staged kernels store through it)
   dim3 grid{};
   int smem_bytes = 0;
   int cg = 1;          // CTAs per MMA (tcgen05 cta_group): 2 = CTA pairs in 2-CTA clusters
+  int staged = 0;      // 1: out_act leaves through shared memory and TMA stores (conv_tc.cuh, STAGED)
 };
 
 // CTA pairs for the unfused convolutions: only layers with a single N tile (both CTAs of a pair must use the same
@@ -99,10 +101,15 @@ inline int conv_cta_group(const ConvShape& s) {
 // Fill every geometry field of plan.p from the layer shape and the problem size.  `mt_pref` = preferred
 // number of 128-row tiles per unit (1, 2 or 4; reduced until TMEM and shared memory fit); `n_sms` sizes the
 // persistent grid.
-inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pref, int n_sms = 148, int cg = 0) {
+inline int plan_conv_impl(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pref, int n_sms, int cg,
+                          int staged) {
   ConvParams& p = plan.p;
   if (cg == 0) cg = conv_cta_group(s);
   plan.cg = cg;
+  if (staged && (s.nt % 64 != 0 || s.cin == 32)) staged = 0;  // 64-column groups; 128-byte-row kernels only
+  plan.staged = staged;
+  p.staged = staged;
+  const int stage_bytes_out = staged ? kStageBufs * kStageBufBytes : 0;
   if (s.cin != 32 && s.cin % 64 != 0) return fail(-2, "cin must be 32 or a multiple of 64");
   if (s.nt % 32 != 0 || s.nt > 256 || s.n_total % s.nt != 0) return fail(-2, "bad N tiling");
   const int n_tiles = s.n_total / s.nt;
@@ -136,7 +143,7 @@ inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pr
   p.n_chunks = (total_tiles + tpc - 1) / tpc;
   p.stage_bytes = tpc * tile_bytes;
   const int bar_bytes = 512;
-  const int budget = kSmemLimit - 1024 - bar_bytes;
+  const int budget = kSmemLimit - 1024 - bar_bytes - stage_bytes_out;
   int mt0 = mt_pref >= 4 ? 4 : (mt_pref >= 2 ? 2 : 1);
   for (int mt = mt0; mt >= 1; mt >>= 1) {
     if (mt * s.nt > 512) continue;
@@ -159,7 +166,7 @@ inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pr
         p.n_acc = 2 * mt * s.nt <= 512 ? 2 : 1;
         p.tiles_per_b = (T + 128 * mt - 1) / (128 * mt);
         p.n_units = B * p.tiles_per_b * n_tiles;
-        plan.smem_bytes = 1024 + slots * panel_bytes + stages * p.stage_bytes + bar_bytes;
+        plan.smem_bytes = 1024 + slots * panel_bytes + stages * p.stage_bytes + stage_bytes_out + bar_bytes;
         int grid = (p.n_units + cg - 1) / cg * cg;
         if (grid > n_sms) grid = n_sms / cg * cg;
         plan.grid = dim3(grid, 1, 1);
@@ -170,6 +177,14 @@ inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pr
   return fail(-3, "convolution does not fit shared memory / TMEM");
 }
 
+// `staged` = 1 asks for the staged TMA-store epilogue (bf16 output in the natural layout only; the caller then fills
+// plan.tm_out with conv_output_map); layers whose slabs leave no room for the staging buffers fall back to direct stores.
+inline int plan_conv(ConvPlan& plan, const ConvShape& s, int B, int T, int mt_pref, int n_sms = 148, int cg = 0,
+                     int staged = 0) {
+  if (staged && plan_conv_impl(plan, s, B, T, mt_pref, n_sms, cg, 1) == 0) return 0;
+  return plan_conv_impl(plan, s, B, T, mt_pref, n_sms, cg, 0);
+}
+
 // E2E_NO_PDL=1 launches every kernel fully serialised (A/B experiments).
 inline bool pdl_enabled() {
   static int on = -1;
@@ -177,14 +192,27 @@ inline bool pdl_enabled() {
   return on == 1;
 }
 
-typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const ConvParams);
+typedef void (*ConvKernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvParams);
 
-inline ConvKernelFn conv_kernel_for(int rowb, int mt, int cg = 1) {
+template <bool STAGED>
+inline ConvKernelFn conv_kernel_for_t(int rowb, int mt, int cg) {
   if (cg == 2)  // CTA pairs: 64-channel panels only (wide layers)
-    return mt == 4 ? conv_tc_kernel<128, 4, 2> : (mt == 2 ? conv_tc_kernel<128, 2, 2> : conv_tc_kernel<128, 1, 2>);
-  if (rowb == 128)
-    return mt == 4 ? conv_tc_kernel<128, 4, 1> : (mt == 2 ? conv_tc_kernel<128, 2, 1> : conv_tc_kernel<128, 1, 1>);
-  return mt == 4 ? conv_tc_kernel<64, 4, 1> : (mt == 2 ? conv_tc_kernel<64, 2, 1> : conv_tc_kernel<64, 1, 1>);
+    return mt == 4 ? conv_tc_kernel<128, 4, 2, STAGED>
+                   : (mt == 2 ? conv_tc_kernel<128, 2, 2, STAGED> : conv_tc_kernel<128, 1, 2, STAGED>);
+  return mt == 4 ? conv_tc_kernel<128, 4, 1, STAGED>
+                 : (mt == 2 ? conv_tc_kernel<128, 2, 1, STAGED> : conv_tc_kernel<128, 1, 1, STAGED>);
+}
+
+inline ConvKernelFn conv_kernel_for(int rowb, int mt, int cg = 1, int staged = 0) {
+  if (rowb == 128) return staged ? conv_kernel_for_t<true>(rowb, mt, cg) : conv_kernel_for_t<false>(rowb, mt, cg);
+  return mt == 4 ? conv_tc_kernel<64, 4, 1, false>
+                 : (mt == 2 ? conv_tc_kernel<64, 2, 1, false> : conv_tc_kernel<64, 1, 1, false>);
+}
+
+// Fills plan.tm_out for a staged plan (out = the bf16 [B][T][n_total] activation output).
+inline int conv_output_map(ConvPlan& plan, const void* out, int B, int T) {
+  if (!plan.staged) return 0;
+  return make_act_tensor_map(&plan.tm_out, out, B, T, plan.p.n_total, 64, 128);
 }
 
 // Fills plan.tm_w (needed by the CTA-pair form; harmless otherwise).  w = packed image of the layer.
@@ -201,14 +229,15 @@ inline int conv_kernels_init() {
   cudaGetDevice(&dev);
   if (done_for_device == dev) return 0;
   const int rowbs[2] = {128, 64}, mts[3] = {1, 2, 4};
-  for (int cg = 1; cg <= 2; ++cg)
-    for (int r : rowbs)
-      for (int m : mts) {
-        if (cg == 2 && r == 64) continue;
-        cudaError_t e =
-            cudaFuncSetAttribute(conv_kernel_for(r, m, cg), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
-        if (e != cudaSuccess) return fail((int)e, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-      }
+  for (int staged = 0; staged <= 1; ++staged)
+    for (int cg = 1; cg <= 2; ++cg)
+      for (int r : rowbs)
+        for (int m : mts) {
+          if ((cg == 2 || staged) && r == 64) continue;
+          cudaError_t e = cudaFuncSetAttribute(conv_kernel_for(r, m, cg, staged),
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+          if (e != cudaSuccess) return fail((int)e, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+        }
   done_for_device = dev;
   return 0;
 }
@@ -230,7 +259,8 @@ inline int launch_conv(const ConvPlan& plan, cudaStream_t st) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_kernel_for(plan.p.rowb, plan.p.mt, plan.cg), plan.tm, plan.tm_w, plan.p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, conv_kernel_for(plan.p.rowb, plan.p.mt, plan.cg, plan.staged), plan.tm,
+                                     plan.tm_w, plan.tm_out, plan.p);
   if (e != cudaSuccess) return fail((int)e, std::string("conv_tc launch: ") + cudaGetErrorString(e));
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("conv_tc launch: ") + cudaGetErrorString(e));

@@ -40,6 +40,8 @@ constexpr int kMaxTaps = 16;
 constexpr int kMaxNTiles = 16;
 constexpr int kMaxPanelSlots = 8;
 constexpr int kMaxStages = 8;
+constexpr int kStageBufs = 2;             // staged-store buffers (STAGED kernels)
+constexpr int kStageBufBytes = 128 * 128; // one 128-row x 64-column bf16 tile, SWIZZLE_128B
 
 struct ConvParams {
   int T;                // time steps per utterance (rows); input and output have the same row count
@@ -67,6 +69,7 @@ struct ConvParams {
   int act_tanh;         // 1: out_act = tanh(result) instead (Postnet)
   int sum_tiled;        // sum_a is in the tiled8 layout (epilogue.cuh)
   int out_tiled;        // out_act is written in the tiled8 layout
+  int staged;           // == template STAGED: out_act leaves through shared memory and TMA stores (see the kernel)
   int8_t shift[kMaxNTiles][kMaxTaps];  // row shift of each tap, per N tile
   const uint8_t* w;     // packed weights
   const float* bias;    // [n_total]
@@ -124,10 +127,10 @@ __device__ unsigned int g_trace2[512][24];
 #define E2E_TR2_FLUSH
 #endif
 
-template <int ROWB, int MT, int CG>
+template <int ROWB, int MT, int CG, bool STAGED>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
-               const ConvParams p) {
+               const __grid_constant__ CUtensorMap tm_out, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -152,14 +155,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 
   uint8_t* slabs = smem;
   uint8_t* ring = slabs + p.panel_slots * panel_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + p.n_stages * p.stage_bytes);
+  uint8_t* stage_buf = ring + p.n_stages * p.stage_bytes;  // [kStageBufs][kStageBufBytes] when STAGED
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_buf + (STAGED ? kStageBufs * kStageBufBytes : 0));
   uint64_t* panel_full = bars;                          // [kMaxPanelSlots]
   uint64_t* panel_empty = panel_full + kMaxPanelSlots;  // [kMaxPanelSlots]
   uint64_t* w_full = panel_empty + kMaxPanelSlots;      // [kMaxStages]
   uint64_t* w_empty = w_full + kMaxStages;              // [kMaxStages]
   uint64_t* acc_full = w_empty + kMaxStages;            // [2]
   uint64_t* acc_empty = acc_full + 2;                   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* stage_full = acc_empty + 2;                 // [kStageBufs] staged tile written by all epilogue warps
+  uint64_t* stage_free = stage_full + kStageBufs;       // [kStageBufs] the TMA store has read the tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + kStageBufs);
 
   if (threadIdx.x == 0) {
     E2E_TR(0);
@@ -178,6 +184,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], kEpiWarps * CG);  // (the even CTA's copy collects both CTAs' epilogue warps)
+    }
+    for (int i = 0; i < kStageBufs; ++i) {
+      mbar_init(&stage_full[i], kEpiWarps);
+      mbar_init(&stage_free[i], 1);
     }
     fence_mbar_init();
   }
@@ -348,6 +358,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       }
     }
     if (leader) E2E_TR(4);
+  } else if (warp == 3) {
+    if (STAGED && lane == 0) {
+      // ---------------- store warp (STAGED): staged 128-row x 64-column tiles -> global memory by TMA ----------
+      // The epilogue warps leave each group of four 16-column items (one 64-column panel of one M tile) in a
+      // SWIZZLE_128B staging buffer; this thread writes it with one bulk-tensor store (rows past the utterance end
+      // are clipped by the TMA unit).  A thread's own global stores would be 32 bytes per lane at a row pitch of
+      // 2 * n_total bytes - ~64 L1 wavefronts per warp access on the data pipe the tensor core's operand reads need.
+      griddep_wait();
+      tma_prefetch_desc(&tm_out);
+      const int groups = MT * (p.nt >> 6), gpm = p.nt >> 6;
+      uint32_t gi = 0;
+      UnitIter uit;
+      uit.init(u_first, u_step, p.n_tiles, p.tiles_per_b);
+      for (int n = 0; n < N; ++n, uit.next()) {
+        const int t0 = uit.tile * (128 * MT);
+        for (int g = 0; g < groups; ++g, ++gi) {
+          const uint32_t buf = gi % kStageBufs, par = (gi / kStageBufs) & 1;
+          mbar_wait(&stage_full[buf], par, 0x800 + buf);
+          const int m = g / gpm, pn = g - m * gpm;
+          if (uit.b < p.B && t0 + m * 128 < p.T) {
+            tma_store_3d(&tm_out, stage_buf + buf * kStageBufBytes, uit.nti * p.nt + pn * 64, t0 + m * 128, uit.b);
+            bulk_commit_group();
+            bulk_wait_group_read<0>();
+          }
+          mbar_arrive(&stage_free[buf]);
+        }
+      }
+      bulk_wait_group<0>();
+    }
   } else if (warp >= 4) {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
     griddep_wait();  // residual / running-sum reads and every output store follow the previous kernel
@@ -366,6 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     eo.inv = p.res_inv_slope;
     eo.act_tanh = p.act_tanh;
     uint32_t it = 0, acc = 0, apar = 0;
+    uint32_t gi = 0;  // STAGED: running count of 64-column groups (the staging ring position)
     UnitIter uit;
     uit.init(u_first, u_step, p.n_tiles, p.tiles_per_b);
     for (int n = 0; n < N; ++n, ++it, uit.next()) {
@@ -415,7 +455,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
         tmem_ld_wait();
-        epi_finish16(v, bv, rq, sa, eo, (p.out_tiled && valid) ? tiled_off(item, n0) : off, valid);
+        if (STAGED) {
+          // item = 4 * group + part: this warp's 16 columns of the group's 64-column tile, in the tile's swizzled layout
+          uint32_t pk[8];
+          epi_compute16(v, bv, rq, sa, eo, pk);
+          const uint32_t buf = gi % kStageBufs, spar = (gi / kStageBufs) & 1;
+          ++gi;
+          uint32_t so = static_cast<uint32_t>(row_in_tile) * 128 + (cc & 3) * 32;
+          so ^= ((so >> 7) & 7u) << 4;
+          so += smem_u32(stage_buf) + buf * kStageBufBytes;
+          mbar_wait(&stage_free[buf], spar ^ 1, 0x880 + buf);  // the previous tile in this buffer has been read
+          st_shared_u4(so, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          st_shared_u4(so ^ 16u, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+          fence_proxy_async_smem();  // the TMA unit reads the tile through the async proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&stage_full[buf]);
+        } else {
+          epi_finish16(v, bv, rq, sa, eo, (p.out_tiled && valid) ? tiled_off(item, n0) : off, valid);
+        }
         prefetch(item + 8, rq, sa);  // refill this slot for the item after next
       };
       for (int item = part; item < items; item += 8) {

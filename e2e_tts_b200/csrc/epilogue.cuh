@@ -131,6 +131,14 @@ __device__ __forceinline__ void epi_compute16(const uint32_t (&v)[16], const flo
     for (int i = 0; i < 16; ++i) f[i] *= sc;
   }
   const float s = o.slope;
+  if (o.act_tanh) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(tanhf(f[2 * i]), tanhf(f[2 * i + 1]));
+      pk[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float a = f[2 * i], c = f[2 * i + 1];

@@ -360,9 +360,18 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
       mt = cand;
     }
   }
-  int rc = plan_conv(op.plan, s, B, T, mt, v->n_sms);
+  // Staged TMA stores of the bf16 output (conv_tc.cuh, STAGED): natural-layout bf16 outputs only, and only where
+  // the epilogue rather than the MMAs bounds the layer - few taps (k = 3 convolutions, the two-tap polyphase
+  // upsamplers).  Measured per launch, 16 x 5 s: C = 256 k = 3 28.3 -> 25.5 us, ups.1 75.6 -> 64.7 us, k >= 7 unchanged,
+  // conv_pre 16.5 -> 18.5 us.  E2E_CONV_STAGED=0|1 forces it off / on wherever it is possible.
+  static const char* est = std::getenv("E2E_CONV_STAGED");
+  const bool can_stage = out_act && !out_f32 && !(tiled & kOutTiled);
+  const int staged = can_stage && (est ? est[0] == '1' : s.taps <= 3);
+  int rc = plan_conv(op.plan, s, B, T, mt, v->n_sms, 0, staged);
   if (rc) return rc;
   ConvParams& p = op.plan.p;
+  rc = conv_output_map(op.plan, out_act, B, T);
+  if (rc) return rc;
   rc = make_act_tensor_map(&op.plan.tm, in, B, T, s.cin, p.rowb / 2, p.box_rows);
   if (rc) return rc;
   p.w = L.d_w;

@@ -108,7 +108,11 @@ int main(int argc, char** argv) {
   const int id = atoi(argv[1]);
   const int reps = argc > 2 ? atoi(argv[2]) : 3;
   if (id < 0 || id >= kNumCfgs) return 1;
-  const Cfg& c = kCfgs[id];
+  Cfg c = kCfgs[id];
+  {  // E2E_CONV_STAGED=1: exercise the staged TMA-store epilogue (bf16 output only) on every configuration that has one
+    const char* est0 = getenv("E2E_CONV_STAGED");
+    if (est0 && est0[0] == '1' && c.actout) c.f32out = 0;
+  }
   printf("[cfg %d] %s: cin=%d N=%d nt=%d taps=%d dil=%d B=%d T=%d mt=%d\n", id, c.name, c.cin, c.n_total, c.nt,
          c.taps, c.dil, c.B, c.T, c.mt);
 
@@ -195,7 +199,9 @@ int main(int argc, char** argv) {
   }
 
   ConvPlan plan;
-  int rc = plan_conv(plan, s, c.B, c.T, c.mt);
+  const char* est = getenv("E2E_CONV_STAGED");
+  const int want_staged = est && est[0] == '1' && c.actout && !c.f32out;
+  int rc = plan_conv(plan, s, c.B, c.T, c.mt, 148, 0, want_staged);
   if (rc) {
     printf("plan_conv failed: %s\n", last_error().c_str());
     return 3;
@@ -218,10 +224,15 @@ int main(int argc, char** argv) {
   p.sum_a = dsum;
   p.out_f32 = dout;
   p.out_act = dact;
+  rc = conv_output_map(plan, dact, c.B, c.T);
+  if (rc) {
+    printf("output tensor map failed: %s\n", last_error().c_str());
+    return 3;
+  }
   p.slope = 0.1f;
   p.divisor = c.div3 ? 3.0f : 0.f;
-  printf("  plan: cg=%d grid=%d units=%d smem=%d mt=%d slab_rows=%d box=%d panel_slots=%d stages=%d stage_bytes=%d chunks=%d n_acc=%d hl=%d\n",
-         plan.cg, plan.grid.x, p.n_units, plan.smem_bytes, p.mt, p.slab_rows, p.box_rows, p.panel_slots, p.n_stages,
+  printf("  plan: staged=%d cg=%d grid=%d units=%d smem=%d mt=%d slab_rows=%d box=%d panel_slots=%d stages=%d stage_bytes=%d chunks=%d n_acc=%d hl=%d\n",
+         plan.staged, plan.cg, plan.grid.x, p.n_units, plan.smem_bytes, p.mt, p.slab_rows, p.box_rows, p.panel_slots, p.n_stages,
          p.stage_bytes, p.n_chunks, p.n_acc, p.hl);
 
   rc = launch_conv(plan, 0);
