@@ -395,6 +395,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     const int part = e >> 2;    // this warp takes the items with item % 4 == part
     const int nchunk = p.nt >> 4;
     const int items = MT * nchunk;  // (m tile, 16-column chunk) pairs
+    // item -> (m tile, chunk) without an integer division when nchunk is a power of two (nt = 32 / 64 / 128 / 256)
+    const bool nc_pow2 = (nchunk & (nchunk - 1)) == 0;
+    const int nc_shift = 31 - __clz(nchunk);
+    auto m_of = [&](int item) -> int { return nc_pow2 ? (item >> nc_shift) : item / nchunk; };
     const int row_in_tile = quarter * 32 + lane;
     EpiOut eo;
     eo.sum_a = p.sum_a;
@@ -417,7 +421,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       // residual and partial sums (16 bf16 each) are fetched one item ahead, before the accumulator is waited on
       uint4 rqa[2], rqb[2], saa[2], sab[2];
       auto item_off = [&](int item, int& n0, bool& valid) -> size_t {
-        const int m = item / nchunk, cc = item - m * nchunk;
+        const int m = m_of(item), cc = item - m * nchunk;
         const int t = t0 + m * 128 + row_in_tile;
         valid = item < items && t < p.T && b < p.B;
         n0 = nti * p.nt + cc * 16;
@@ -425,7 +429,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       };
       const int t8 = (p.T + 7) >> 3, c16 = p.n_total >> 4;
       auto tiled_off = [&](int item, int n0) -> size_t {
-        const int m = item / nchunk;
+        const int m = m_of(item);
         return tiled8_off(b, t0 + m * 128 + row_in_tile, n0 >> 4, t8, c16);
       };
       auto prefetch = [&](int item, uint4 (&rq)[2], uint4 (&sa)[2]) {
@@ -445,7 +449,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       if (it == 0 && threadIdx.x == 128) E2E_TR(5);
 
       auto process = [&](int item, uint4 (&rq)[2], uint4 (&sa)[2]) {
-        const int m = item / nchunk, cc = item - m * nchunk;
+        const int m = m_of(item), cc = item - m * nchunk;
         int n0;
         bool valid;
         const size_t off = item_off(item, n0, valid);

@@ -37,7 +37,7 @@ inline bool pair_supported(int C, int k, int d) {
   return (C == 32 || C == 64 || C == 128) && (k & 1) && k <= kMaxTaps && (k - 1) * d <= 120;
 }
 
-constexpr int kPairTailBytes = 512 + 1024;  // mbarriers + the two staged bias vectors
+constexpr int kPairTailBytes = 512 + 1024;  // mbarriers (+ 1 KB spare; the biases are kernel parameters)
 
 inline int plan_pair(PairPlan& plan, int C, int k, int d, int B, int T, int n_sms = 148) {
   if (!pair_supported(C, k, d)) return fail(-2, "fused pair: unsupported channel count / kernel size");

@@ -50,8 +50,8 @@ struct PairParams {
   float res_inv_slope;  // 1 / slope of the stored input activation
   const uint8_t* w1;    // packed weights of c1 / c2: [panel][tap][nt][rowb] swizzled images
   const uint8_t* w2;
-  const float* bias1;
-  const float* bias2;
+  float bias1[128];     // biases of c1 / c2 (nt <= 128), in the kernel-parameter constant bank: every epilogue warp reads
+  float bias2[128];     // its 16 columns with warp-uniform constant loads, off the shared-memory / L1 data pipe
   const __nv_bfloat16* res_act;  // == the kernel's input tensor (bf16 leaky_relu(x)), read for the residual
   const __nv_bfloat16* sum_a;    // bf16 running sum over the stage's resblocks (generator.py:44-47) or nullptr
   int sum_tiled;                 // sum_a is in the tiled8 layout (epilogue.cuh)
@@ -63,7 +63,7 @@ template <int ROWB, int MT, int CG, bool STAGED>
 __global__ void __launch_bounds__(kConvThreads, 1)
 pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w1,
                const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_out,
-               const __grid_constant__ CUtensorMap tm_out2, const PairParams p) {
+               const __grid_constant__ CUtensorMap tm_out2, const __grid_constant__ PairParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -105,8 +105,6 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   uint64_t* stage_full = m_full + 2;          // [2] the c2 epilogue has staged a unit's result in the lane's M slab
   uint64_t* stage_free = stage_full + 2;      // [2] ... and the store warp's TMA store has read it out again
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_free + 2);
-  float* s_bias1 = reinterpret_cast<float*>(bars + 64);  // [nt] biases of c1 / c2, staged once (512 B past `bars`)
-  float* s_bias2 = s_bias1 + 128;
 
   // units of this CTA: u_n = CG * (cluster + n * n_clusters) + rank, n = 0 .. N-1.  N is the same for both CTAs of
   // a pair; a unit index >= n_units is a dummy (utterance index B: TMA zero-fills, nothing is stored).
@@ -151,10 +149,6 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       tmem_alloc(tmem_slot, 512);
       tmem_relinquish();
     }
-  }
-  for (int i = threadIdx.x; i < p.nt; i += blockDim.x) {
-    s_bias1[i] = p.bias1[i];
-    s_bias2[i] = p.bias2[i];
   }
   tc_fence_before_sync();
   if (CG == 2) cluster_sync_all();  // the peer's mbarriers are initialised before anything arrives on them
@@ -411,7 +405,8 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     };
     auto lds_bias = [&](const float* sb, int cc, float4 (&bv)[4]) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) bv[i] = *reinterpret_cast<const float4*>(sb + cc * 16 + 4 * i);
+      for (int i = 0; i < 4; ++i)
+        bv[i] = make_float4(sb[cc * 16 + 4 * i], sb[cc * 16 + 4 * i + 1], sb[cc * 16 + 4 * i + 2], sb[cc * 16 + 4 * i + 3]);
     };
 
     // c1 epilogue.  The TMEM load of the second item is in flight while the first item is processed; the bias
@@ -434,13 +429,13 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       uint32_t vA[16], vB[16];
       float4 bv[4];
       tmem_ld_32x16(d_tmem + mA * p.nt + ccA * 16, vA);
-      lds_bias(s_bias1, ccA, bv);
+      lds_bias(p.bias1, ccA, bv);
       tmem_ld_wait();
       E2E_TR2(3);
       tmem_ld_32x16(d_tmem + mB * p.nt + ccB * 16, vB);
       store_mid(vA, bv, mA, ccA, t0, mdst);
       E2E_TR2(4);
-      lds_bias(s_bias1, ccB, bv);
+      lds_bias(p.bias1, ccB, bv);
       tmem_ld_wait();
       E2E_TR2(5);
       store_mid(vB, bv, mB, ccB, t0, mdst);
@@ -524,7 +519,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       uint32_t vA[16], vB[16], pk[8];
       float4 bv[4];
       tmem_ld_32x16(d_tmem + mA * p.nt + ccA * 16, vA);
-      lds_bias(s_bias2, ccA, bv);
+      lds_bias(p.bias2, ccA, bv);
       tmem_ld_wait();
       E2E_TR2(9);
       tmem_ld_32x16(d_tmem + mB * p.nt + ccB * 16, vB);
@@ -536,7 +531,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         epi_finish16(vA, bv, rqa, sqa, eo, offa, va);
       }
       E2E_TR2(10);
-      lds_bias(s_bias2, ccB, bv);
+      lds_bias(p.bias2, ccB, bv);
       tmem_ld_wait();
       E2E_TR2(11);
       // every TMEM read of this warp has completed: release the accumulator

@@ -23,6 +23,7 @@ struct Layer {
   ConvShape shape;           // GEMM form (L_CONV / L_CONVT)
   uint8_t* d_w = nullptr;    // packed bf16 weights (or fp32 [k][cin] for L_POST)
   float* d_bias = nullptr;   // [n_total]
+  std::vector<float> h_bias;  // host copy (the fused pair kernel takes its biases as kernel parameters)
   float post_bias = 0.f;
   bool loaded = false;
 };
@@ -286,6 +287,7 @@ extern "C" int e2e_voc_load_layer(e2e_voc* v, const char* name, const float* wei
     return fail((int)e, "cudaMemcpy");
   if ((e = cudaMemcpy(L.d_bias, bg.data(), bg.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
     return fail((int)e, "cudaMemcpy");
+  L.h_bias = bg;
   L.loaded = true;
   v->plans.clear();
   return 0;
@@ -409,8 +411,9 @@ static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B,
   p.w2 = L2.d_w;
   rc = pair_weight_maps(op.pair, L1.d_w, L2.d_w);
   if (rc) return rc;
-  p.bias1 = L1.d_bias;
-  p.bias2 = L2.d_bias;
+  if (L1.h_bias.size() > 128 || L2.h_bias.size() > 128) return fail(-2, "fused pair: more than 128 channels");
+  std::copy(L1.h_bias.begin(), L1.h_bias.end(), p.bias1);
+  std::copy(L2.h_bias.begin(), L2.h_bias.end(), p.bias2);
   p.res_act = in;
   p.res_inv_slope = 10.0f;
   p.sum_a = sum_a;

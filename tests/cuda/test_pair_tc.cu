@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <random>
+#include <algorithm>
 #include <vector>
 #include "../../e2e_tts_b200/csrc/pair_host.cuh"
 
@@ -182,8 +183,8 @@ int main(int argc, char** argv) {
     printf("weight tensor maps failed: %s\n", last_error().c_str());
     return 3;
   }
-  p.bias1 = db1;
-  p.bias2 = db2;
+  std::copy(hb1.begin(), hb1.end(), p.bias1);
+  std::copy(hb2.begin(), hb2.end(), p.bias2);
   p.res_act = dx;
   p.res_inv_slope = 10.0f;
   p.sum_a = dsum;
