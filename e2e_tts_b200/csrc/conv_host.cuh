@@ -2,6 +2,7 @@
 // so the library does not link libcuda), launch-plan sizing and the weight packer that writes the swizzled
 // shared-memory images the kernel streams with 1-D bulk copies.
 #pragma once
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -207,6 +208,14 @@ inline ConvKernelFn conv_kernel_for(int rowb, int mt, int cg = 1, int staged = 0
   if (rowb == 128) return staged ? conv_kernel_for_t<true>(rowb, mt, cg) : conv_kernel_for_t<false>(rowb, mt, cg);
   return mt == 4 ? conv_tc_kernel<64, 4, 1, false>
                  : (mt == 2 ? conv_tc_kernel<64, 2, 1, false> : conv_tc_kernel<64, 1, 1, false>);
+}
+
+// Bias of the layer: host copy into the kernel parameters when it fits, device pointer otherwise.
+inline void conv_set_bias(ConvPlan& plan, const float* d_bias, const float* h_bias, int n) {
+  ConvParams& p = plan.p;
+  p.bias = d_bias;
+  p.bias_const = h_bias != nullptr && n <= kMaxBiasConst;
+  if (p.bias_const) std::copy(h_bias, h_bias + n, p.cbias);
 }
 
 // Fills plan.tm_out for a staged plan (out = the bf16 [B][T][n_total] activation output).

@@ -40,6 +40,7 @@ constexpr int kMaxTaps = 16;
 constexpr int kMaxNTiles = 16;
 constexpr int kMaxPanelSlots = 8;
 constexpr int kMaxStages = 8;
+constexpr int kMaxBiasConst = 2048;       // biases up to this many columns travel as kernel parameters (constant bank)
 constexpr int kStageBufs = 2;             // staged-store buffers (STAGED kernels)
 constexpr int kStageBufBytes = 128 * 128; // one 128-row x 64-column bf16 tile, SWIZZLE_128B
 
@@ -72,7 +73,9 @@ struct ConvParams {
   int staged;           // == template STAGED: out_act leaves through shared memory and TMA stores (see the kernel)
   int8_t shift[kMaxNTiles][kMaxTaps];  // row shift of each tap, per N tile
   const uint8_t* w;     // packed weights
-  const float* bias;    // [n_total]
+  const float* bias;    // [n_total] (device memory: used when n_total > kMaxBiasConst)
+  int bias_const;       // 1: cbias holds the bias - warp-uniform constant-bank loads, off the L1 data pipe the
+  float cbias[kMaxBiasConst];  // tensor core's operand reads and every other epilogue access share
   const __nv_bfloat16* res_act;  // bf16 [B][T][n_total] = leaky_relu(x, 1/res_inv_slope) of the residual x of
                                  // `xt + x` (layers.py:39), or nullptr; x is recovered by the inverse LeakyReLU
   float res_inv_slope;  // 1 / slope used when res_act was written (10 for LRELU_SLOPE = 0.1)
@@ -130,7 +133,7 @@ __device__ unsigned int g_trace2[512][24];
 template <int ROWB, int MT, int CG, bool STAGED>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_w,
-               const __grid_constant__ CUtensorMap tm_out, const ConvParams p) {
+               const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -456,8 +459,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         uint32_t v[16];
         tmem_ld_32x16(d_tmem + m * p.nt + cc * 16, v);
         float4 bv[4];  // the bias loads are in flight together with the TMEM load
+        if (p.bias_const) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+          for (int i = 0; i < 4; ++i)
+            bv[i] = make_float4(p.cbias[n0 + 4 * i], p.cbias[n0 + 4 * i + 1], p.cbias[n0 + 4 * i + 2], p.cbias[n0 + 4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);
+        }
         tmem_ld_wait();
         if (STAGED) {
           // item = 4 * group + part: this warp's 16 columns of the group's 64-column tile, in the tile's swizzled layout
