@@ -210,12 +210,21 @@ inline ConvKernelFn conv_kernel_for(int rowb, int mt, int cg = 1, int staged = 0
                  : (mt == 2 ? conv_tc_kernel<64, 2, 1, false> : conv_tc_kernel<64, 1, 1, false>);
 }
 
-// Bias of the layer: host copy into the kernel parameters when it fits, device pointer otherwise.
-inline void conv_set_bias(ConvPlan& plan, const float* d_bias, const float* h_bias, int n) {
+// Bias of the layer: host copy into the kernel parameters when it fits, device pointer otherwise.  `period` > 0: the
+// bias repeats every `period` columns (polyphase ConvTranspose: column p * C_out + co) - only one period is passed.
+inline void conv_set_bias(ConvPlan& plan, const float* d_bias, const float* h_bias, int n, int period = 0) {
   ConvParams& p = plan.p;
   p.bias = d_bias;
-  p.bias_const = h_bias != nullptr && n <= kMaxBiasConst;
-  if (p.bias_const) std::copy(h_bias, h_bias + n, p.cbias);
+  p.bias_const = 0;
+  p.bias_mask = 0x7fffffff;
+  if (!h_bias) return;
+  if (period >= 16 && period < n && (period & (period - 1)) == 0 && n % period == 0 && period <= kMaxBiasConst) {
+    p.bias_mask = period - 1;
+    n = period;
+  }
+  if (n > kMaxBiasConst) return;
+  p.bias_const = 1;
+  std::copy(h_bias, h_bias + n, p.cbias);
 }
 
 // Fills plan.tm_out for a staged plan (out = the bf16 [B][T][n_total] activation output).

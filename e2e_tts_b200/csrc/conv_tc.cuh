@@ -40,7 +40,7 @@ constexpr int kMaxTaps = 16;
 constexpr int kMaxNTiles = 16;
 constexpr int kMaxPanelSlots = 8;
 constexpr int kMaxStages = 8;
-constexpr int kMaxBiasConst = 2048;       // biases up to this many columns travel as kernel parameters (constant bank)
+constexpr int kMaxBiasConst = 512;        // biases up to this many columns travel as kernel parameters (constant bank)
 constexpr int kStageBufs = 2;             // staged-store buffers (STAGED kernels)
 constexpr int kStageBufBytes = 128 * 128; // one 128-row x 64-column bf16 tile, SWIZZLE_128B
 
@@ -75,7 +75,8 @@ struct ConvParams {
   const uint8_t* w;     // packed weights
   const float* bias;    // [n_total] (device memory: used when n_total > kMaxBiasConst)
   int bias_const;       // 1: cbias holds the bias - warp-uniform constant-bank loads, off the L1 data pipe the
-  float cbias[kMaxBiasConst];  // tensor core's operand reads and every other epilogue access share
+  int bias_mask;        //    tensor core's operand reads and every other epilogue access share; column n reads
+  float cbias[kMaxBiasConst];  // cbias[n & bias_mask] (the polyphase upsamplers repeat C_out biases per phase)
   const __nv_bfloat16* res_act;  // bf16 [B][T][n_total] = leaky_relu(x, 1/res_inv_slope) of the residual x of
                                  // `xt + x` (layers.py:39), or nullptr; x is recovered by the inverse LeakyReLU
   float res_inv_slope;  // 1 / slope used when res_act was written (10 for LRELU_SLOPE = 0.1)
@@ -460,9 +461,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         tmem_ld_32x16(d_tmem + m * p.nt + cc * 16, v);
         float4 bv[4];  // the bias loads are in flight together with the TMEM load
         if (p.bias_const) {
+          const int nb = n0 & p.bias_mask;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            bv[i] = make_float4(p.cbias[n0 + 4 * i], p.cbias[n0 + 4 * i + 1], p.cbias[n0 + 4 * i + 2], p.cbias[n0 + 4 * i + 3]);
+            bv[i] = make_float4(p.cbias[nb + 4 * i], p.cbias[nb + 4 * i + 1], p.cbias[nb + 4 * i + 2], p.cbias[nb + 4 * i + 3]);
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + i);

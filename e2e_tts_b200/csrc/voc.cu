@@ -379,7 +379,7 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
   p.w = L.d_w;
   rc = conv_weight_map(op.plan, L.d_w);
   if (rc) return rc;
-  conv_set_bias(op.plan, L.d_bias, L.h_bias.data(), (int)L.h_bias.size());
+  conv_set_bias(op.plan, L.d_bias, L.h_bias.data(), (int)L.h_bias.size(), L.kind == L_CONVT ? L.cout : 0);
   p.res_act = res_act;
   p.res_inv_slope = 10.0f;  // 1 / LRELU_SLOPE: every residual tensor was written with slope 0.1
   p.sum_a = sum_a;

@@ -218,7 +218,7 @@ int main(int argc, char** argv) {
     printf("weight tensor map failed: %s\n", last_error().c_str());
     return 3;
   }
-  conv_set_bias(plan, db, getenv("E2E_CONV_BIAS_GLOBAL") ? nullptr : hb.data(), c.n_total);
+  conv_set_bias(plan, db, getenv("E2E_CONV_BIAS_GLOBAL") ? nullptr : hb.data(), c.n_total);  // (random per column: no period)
   p.res_act = dres;
   p.res_inv_slope = 10.0f;
   p.sum_a = dsum;
