@@ -47,7 +47,9 @@ inline int plan_pair(PairPlan& plan, int C, int k, int d, int B, int T, int n_sm
   plan.cg = pair_cta_group(C, k);
   {
     const char* e = std::getenv("E2E_PAIR_STAGED");   // 0 | 1 overrides for experiments
-    plan.staged = e ? (e[0] == '1' && C >= 64) : (C >= 64 && k <= 3);
+    // Off by default since the biases moved to the constant bank: per launch, staged -> direct stores,
+    // C = 128 k = 3 111.5 -> 105.8 us, C = 64 k = 3 95 -> 82.5 us (before that change staged won: 125 -> 111, 106 -> 100).
+    plan.staged = e ? (e[0] == '1' && C >= 64) : false;
   }
   const int rowb = plan.rowb, mt = plan.mt, cg = plan.cg;
   p.T = T;
