@@ -18,10 +18,10 @@
 //   warp 1   weight producer: bulk copies into the weight ring
 //   warp 2   MMA issuer     : one thread issues tcgen05.mma; the (M tile, K step) loops are unrolled and the
 //                             descriptors are advanced by adding to their low word only
-//   warp 3   TMEM allocator
+//   warp 3   TMEM allocator; in STAGED kernels also the store warp (TMA bulk-tensor stores of staged output tiles)
 //   warps 4-19 epilogue     : tcgen05.ld the fp32 accumulators (four warps per TMEM lane quarter, 16-column
-//                             items), fuse bias, residual add (prefetched while the MMAs run), resblock sum,
-//                             /3, LeakyReLU, casts (epilogue.cuh)
+//                             items), fuse bias (kernel parameters = constant bank), residual add (prefetched
+//                             while the MMAs run), resblock sum, /3, LeakyReLU, casts (epilogue.cuh)
 // Accumulators are double-buffered in TMEM when 2*MT*nt <= 512 columns, so the epilogue of unit i overlaps
 // the MMAs of unit i+1.
 //

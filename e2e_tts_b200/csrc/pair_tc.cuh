@@ -16,8 +16,8 @@
 // single MMA-issuing warp walks the software-pipelined job order
 //     c1(u0) | c1(u1) c2(u0) | c1(u2) c2(u1) | ... | c2(u_last)
 // so the epilogue of every job overlaps the MMAs of the next one.  Roles: warp 0 slab producer (TMA), warp 1
-// weight producer (bulk copies, both convs, job order), warp 2 MMA issuer, warp 3 TMEM allocator, warps 4-19
-// epilogue (four per TMEM lane quarter, 16-column items, epilogue.cuh).
+// weight producer (bulk copies, both convs, job order), warp 2 MMA issuer, warp 3 TMEM allocator (and, in
+// STAGED kernels, the store warp), warps 4-19 epilogue (four per TMEM lane quarter, 16-column items, epilogue.cuh).
 //
 // CG = 2 runs the same pipeline on a CTA PAIR (2-CTA cluster, tcgen05 cta_group::2): each CTA owns its units, its
 // slabs and its epilogue, but one thread of the even CTA issues M = 256 MMAs whose rows 0-127 / 128-255 are the two
@@ -403,14 +403,14 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
     };
-    auto lds_bias = [&](const float* sb, int cc, float4 (&bv)[4]) {
+    auto param_bias = [&](const float* sb, int cc, float4 (&bv)[4]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         bv[i] = make_float4(sb[cc * 16 + 4 * i], sb[cc * 16 + 4 * i + 1], sb[cc * 16 + 4 * i + 2], sb[cc * 16 + 4 * i + 3]);
     };
 
     // c1 epilogue.  The TMEM load of the second item is in flight while the first item is processed; the bias
-    // comes from shared memory while the TMEM loads are in flight.
+    // comes from the kernel parameters (constant bank) - no shared-memory or L1 access.
     auto epi1 = [&](int n, int t0) {
       const int ln = n & 1;
       const uint32_t par = (n >> 1) & 1;
@@ -429,13 +429,13 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       uint32_t vA[16], vB[16];
       float4 bv[4];
       tmem_ld_32x16(d_tmem + mA * p.nt + ccA * 16, vA);
-      lds_bias(p.bias1, ccA, bv);
+      param_bias(p.bias1, ccA, bv);
       tmem_ld_wait();
       E2E_TR2(3);
       tmem_ld_32x16(d_tmem + mB * p.nt + ccB * 16, vB);
       store_mid(vA, bv, mA, ccA, t0, mdst);
       E2E_TR2(4);
-      lds_bias(p.bias1, ccB, bv);
+      param_bias(p.bias1, ccB, bv);
       tmem_ld_wait();
       E2E_TR2(5);
       store_mid(vB, bv, mB, ccB, t0, mdst);
@@ -519,7 +519,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       uint32_t vA[16], vB[16], pk[8];
       float4 bv[4];
       tmem_ld_32x16(d_tmem + mA * p.nt + ccA * 16, vA);
-      lds_bias(p.bias2, ccA, bv);
+      param_bias(p.bias2, ccA, bv);
       tmem_ld_wait();
       E2E_TR2(9);
       tmem_ld_32x16(d_tmem + mB * p.nt + ccB * 16, vB);
@@ -531,7 +531,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         epi_finish16(vA, bv, rqa, sqa, eo, offa, va);
       }
       E2E_TR2(10);
-      lds_bias(p.bias2, ccB, bv);
+      param_bias(p.bias2, ccB, bv);
       tmem_ld_wait();
       E2E_TR2(11);
       // every TMEM read of this warp has completed: release the accumulator
