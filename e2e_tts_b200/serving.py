@@ -6,9 +6,20 @@ The reference's loop is strictly serial per batch (e2e_tts/src/api/utils.py:130-
 `.detach().cpu().numpy()`); this is new surface around the same `HifiGan.forward` / `forward_pcm16` call."""
 from __future__ import annotations
 
+import inspect
 from typing import Callable, List, Optional
 
 import torch
+
+
+def _accepts_out(fn) -> bool:
+    """Does the callable take an `out=` keyword (HifiGan.forward / forward_pcm16 do; a plain callable may not)?"""
+    target = fn.forward if isinstance(fn, torch.nn.Module) else fn
+    try:
+        params = inspect.signature(target).parameters
+    except (TypeError, ValueError):
+        return False
+    return "out" in params or any(p.kind is inspect.Parameter.VAR_KEYWORD for p in params.values())
 
 
 class HostPipeline:
@@ -35,7 +46,7 @@ class HostPipeline:
         self._mel_dev: List[Optional[torch.Tensor]] = [None] * self.depth
         self._wav_dev: List[Optional[torch.Tensor]] = [None] * self.depth   # preallocated results (no allocator traffic)
         self._ev_copied: List[Optional[torch.cuda.Event]] = [None] * self.depth
-        self._takes_out = True
+        self._takes_out = _accepts_out(vocoder)
         self._ev_in = [torch.cuda.Event() for _ in range(self.depth)]
         self._ev_comp = [torch.cuda.Event() for _ in range(self.depth)]
         self._ev_out: List[torch.cuda.Event] = []
@@ -48,27 +59,29 @@ class HostPipeline:
         i, slot = self._n, self._n % self.depth
         compute = torch.cuda.current_stream(self.device)
         buf = self._mel_dev[slot]
-        if buf is None or buf.shape != mel_host.shape or buf.dtype != mel_host.dtype:
+        fresh = buf is None or buf.shape != mel_host.shape or buf.dtype != mel_host.dtype
+        if fresh:
             buf = torch.empty(mel_host.shape, dtype=mel_host.dtype, device=self.device)
             self._mel_dev[slot] = buf
+            if self._wav_dev[slot] is not None:                # the cached result has the old batch's shape: drop it,
+                self._wav_dev[slot].record_stream(self.s_out)  # but not before its copy-out has finished reading it
+                self._wav_dev[slot] = None
         with torch.cuda.stream(self.s_in):
             if i >= self.depth:
-                self.s_in.wait_event(self._ev_comp[slot])      # the forward that read this input buffer is done
-            else:
-                self.s_in.wait_stream(compute)                 # the buffer was just allocated on the compute stream
+                self.s_in.wait_event(self._ev_comp[slot])      # the forward that read this slot's input buffer is done
+            if fresh:
+                # a block the caching allocator hands out may have been freed on the compute stream only a moment ago
+                # (e.g. a vocoder workspace still in use by the forward in flight): order the copy after that stream
+                self.s_in.wait_stream(compute)
             buf.copy_(mel_host, non_blocking=True)
             self._ev_in[slot].record(self.s_in)
         compute.wait_event(self._ev_in[slot])
         if self._ev_copied[slot] is not None:
             compute.wait_event(self._ev_copied[slot])          # the previous result in this slot has left the device
         with torch.no_grad():
-            wav = None
             if self._takes_out:
-                try:
-                    wav = self.vocoder(buf, out=self._wav_dev[slot])
-                except TypeError:                              # a plain callable without `out=`
-                    self._takes_out = False
-            if wav is None:
+                wav = self.vocoder(buf, out=self._wav_dev[slot])
+            else:
                 wav = self.vocoder(buf)
         self._wav_dev[slot] = wav if self._takes_out else None
         flat = wav.squeeze(1) if wav.dim() == 3 else wav

@@ -39,6 +39,13 @@ def init_weights(m, mean: float = 0.0, std: float = 0.01) -> None:
         m.weight.data.normal_(mean, std)
 
 
+def apply_weight_norm(m) -> None:
+    """function.py:10-13: `torch.nn.utils.weight_norm` on every Conv* module (used with `module.apply`)."""
+    classname = m.__class__.__name__
+    if classname.find("Conv") != -1:
+        torch.nn.utils.weight_norm(m)
+
+
 class _WNConv(nn.Module):
     """Parameter holder with the reference's weight-norm naming.  `transposed` selects ConvTranspose1d's
     [C_in, C_out, k] weight layout (weight-norm dim 0 is then C_in)."""
@@ -136,6 +143,7 @@ class HifiGan(nn.Module):
         self._handle = None          # e2e_voc* (created lazily on the first CUDA forward)
         self._handle_device = None
         self._loaded_version = None  # parameter-version fingerprint the packed weights correspond to
+        self._param_cache = None
         self._workspaces: Dict[tuple, torch.Tensor] = {}
         self._profile_events = None  # (cudaEvent_t, cudaEvent_t) handles for the next forward (measurement hook)
 
@@ -180,7 +188,7 @@ class HifiGan(nn.Module):
                 g = sd.pop(name + ".weight_g").detach().float()
                 sd[wkey] = v * (g / v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, 1, 1))
         res = super().load_state_dict(sd, strict=strict, **kw)
-        self._loaded_version = None
+        self.invalidate()
         return res
 
     def remove_weight_norm(self) -> None:
@@ -192,7 +200,7 @@ class HifiGan(nn.Module):
             layer.remove_weight_norm()
         self.conv_pre.remove_weight_norm()
         self.conv_post.remove_weight_norm()
-        self._loaded_version = None
+        self.invalidate()
 
     # ------------------------------------------------------------------ native side
     def _native_config(self) -> _native.VocConfig:
@@ -222,7 +230,24 @@ class HifiGan(nn.Module):
         return cfg
 
     def _version_fingerprint(self, device) -> tuple:
-        return (str(device),) + tuple((id(p), p._version) for p in self.parameters())
+        # (id, in-place version counter) of every parameter; the parameter list itself is cached (walking the module
+        # tree costs more than a single-utterance forward) and rebuilt whenever the set of parameters can have changed
+        if self._param_cache is None:
+            self._param_cache = list(self.parameters())
+        return (str(device),) + tuple((id(p), p._version) for p in self._param_cache)
+
+    def invalidate(self) -> None:
+        """Forces the next forward() to re-fold weight-norm and re-pack the device weights.  Needed only after writes
+        the version counters cannot see: `p.data.copy_(...)` / `p.data.normal_()` (what `init_weights` does), or
+        storage shared with an optimizer that updates through `.data`.  Ordinary in-place updates (`p.copy_()`,
+        optimizer steps, `load_state_dict`, `.to()`) are detected automatically."""
+        self._loaded_version = None
+        self._param_cache = None
+
+    def _apply(self, fn, *a, **kw):
+        self._param_cache = None
+        self._loaded_version = None
+        return super()._apply(fn, *a, **kw)
 
     def _sync_native(self, device: torch.device) -> None:
         L = _native.lib()

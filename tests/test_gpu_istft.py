@@ -11,6 +11,7 @@ import torch
 
 import e2e_tts_b200 as pkg
 from oracle import hifigan_oracle as ho
+import margins
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -31,6 +32,7 @@ def check_head(spec, phase, ref_spec, ref_phase, what):
     scale = max(ylog.abs().max().item(), 1.0)
     e1 = (spec.log() - ylog).abs().max().item()
     e2 = (phase - ref_phase.double()).abs().max().item()
+    margins.record(what, log_spec_rel=e1 / scale, phase_rel=e2 / scale, bound=2e-2)
     assert e1 <= 2e-2 * scale, "%s: log-spec err %.3g vs scale %.3g" % (what, e1, scale)
     assert e2 <= 2e-2 * scale, "%s: phase err %.3g vs scale %.3g" % (what, e2, scale)
 

@@ -18,7 +18,8 @@ PAIR_SMALL = list(range(9))                                       # test_pair_tc
 def _run(binary, cfg, env_extra):
     path = os.path.join(BUILD, binary)
     if not os.path.exists(path):
-        pytest.skip("%s not built (scripts/build_cuda_tests.sh)" % binary)
+        pytest.fail("%s not built: __graft_entry__.build() / scripts/build_cuda_tests.sh must run before the GPU suite "
+                    "(a missing binary must not make these tests vanish)" % binary)
     env = dict(os.environ)
     env.update(env_extra)
     r = subprocess.run([path, str(cfg), "1"], env=env, capture_output=True, text=True, timeout=120)
