@@ -11,6 +11,8 @@ from .build import LIB_PATH, build_native
 E2E_MAX_UPSAMPLES = 8
 E2E_MAX_KERNELS = 8
 E2E_MAX_DILATIONS = 8
+E2E_OPERAND_BF16 = 0
+E2E_OPERAND_FP16 = 1
 
 
 class VocConfig(ctypes.Structure):
@@ -45,6 +47,8 @@ SYMBOLS = {
     "e2e_istft_forward": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                   c_void_p]),
     "e2e_voc_set_profile_events": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "e2e_voc_set_operand_dtype": (c_int, [c_void_p, c_int32]),
+    "e2e_voc_operand_dtype": (c_int, [c_void_p]),
     "e2e_voc_hop": (c_int, [c_void_p]),
     "e2e_voc_launches_per_forward": (c_int, [c_void_p]),
     "e2e_postnet_create": (c_int, [c_int32, c_int32, c_int32, c_int32, POINTER(c_void_p)]),

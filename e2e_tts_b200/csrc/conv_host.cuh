@@ -297,6 +297,28 @@ inline uint16_t f32_to_bf16_rn(float f) {
   u += 0x7fffu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
+// fp32 -> fp16 (round to nearest even, saturating to +-65504 like the kernels' cvt.rn.satfinite; NaN kept)
+inline uint16_t f32_to_f16_rn(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7fffffffu;
+  if (x > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);      // NaN
+  if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);     // >= 65520 rounds past the largest finite half: saturate
+  if (x < 0x38800000u) {                                       // below 2^-14: subnormal half (or zero)
+    if (x < 0x33000000u) return (uint16_t)sign;                // < 2^-25 rounds to zero
+    const int shift = 126 - (int)(x >> 23);                    // 14 .. 24 bits to drop
+    uint32_t m = (x & 0x7fffffu) | 0x800000u;
+    const uint32_t rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    m >>= shift;
+    if (rem > half || (rem == half && (m & 1u))) ++m;
+    return (uint16_t)(sign | m);
+  }
+  uint32_t h = ((x - 0x38000000u) >> 13);
+  const uint32_t rem = x & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+  return (uint16_t)(sign | h);
+}
 inline float bf16_to_f32(uint16_t h) {
   uint32_t u = (uint32_t)h << 16;
   float f;
@@ -308,7 +330,7 @@ inline size_t packed_weight_bytes(const ConvShape& s) {
   return (size_t)s.n_total * s.taps * s.cin * 2;
 }
 
-inline void pack_conv_weights(const ConvShape& s, const float* wg, uint8_t* out) {
+inline void pack_conv_weights(const ConvShape& s, const float* wg, uint8_t* out, int f16 = 0) {
   const int rowb = s.cin == 32 ? 64 : 128;
   const int panels = s.cin == 32 ? 1 : s.cin / 64;
   const int chp = rowb / 2;
@@ -323,7 +345,7 @@ inline void pack_conv_weights(const ConvShape& s, const float* wg, uint8_t* out)
           const float* src = wg + ((size_t)(nti * s.nt + r) * s.taps + tap) * s.cin + pn * chp;
           for (int c = 0; c < chp; ++c) {
             const uint32_t off = swizzle_off((uint32_t)(r * rowb + c * 2), mask);
-            const uint16_t h = f32_to_bf16_rn(src[c]);
+            const uint16_t h = f16 ? f32_to_f16_rn(src[c]) : f32_to_bf16_rn(src[c]);
             memcpy(tile + off, &h, 2);
           }
         }

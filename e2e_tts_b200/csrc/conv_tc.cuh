@@ -70,6 +70,7 @@ struct ConvParams {
   int act_tanh;         // 1: out_act = tanh(result) instead (Postnet)
   int sum_tiled;        // sum_a is in the tiled8 layout (epilogue.cuh)
   int out_tiled;        // out_act is written in the tiled8 layout
+  int f16;              // 16-bit tensors and operands are fp16 instead of bf16 (ptx.cuh pack16)
   int staged;           // == template STAGED: out_act leaves through shared memory and TMA stores (see the kernel)
   int8_t shift[kMaxNTiles][kMaxTaps];  // row shift of each tap, per N tile
   const uint8_t* w;     // packed weights
@@ -280,7 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     // The whole warp runs the loop (warp-uniform control flow and address arithmetic); one elected lane issues
     // the tcgen05 instructions.  No divisions: ring positions are counters that wrap.
     const bool leader = elect_one();
-    const uint32_t idesc = umma_idesc_bf16(128 * CG, p.nt);
+    const uint32_t idesc = umma_idesc_bf16(128 * CG, p.nt, p.f16);
     auto wait_full = [&](uint64_t* bar, uint32_t par, uint32_t code) {
       if (CG == 2) mbar_wait_cluster(bar, par, code);
       else mbar_wait(bar, par, code);
@@ -412,6 +413,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     eo.scale = p.divisor != 0.f ? 1.0f / p.divisor : 0.f;
     eo.inv = p.res_inv_slope;
     eo.act_tanh = p.act_tanh;
+    eo.f16 = p.f16;
     uint32_t it = 0, acc = 0, apar = 0;
     uint32_t gi = 0;  // STAGED: running count of 64-column groups (the staging ring position)
     UnitIter uit;

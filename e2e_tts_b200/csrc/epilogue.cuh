@@ -72,14 +72,17 @@ struct EpiOut {
   __nv_bfloat16* out_act;
   float slope, scale, inv;  // scale: 0 = none, else result *= scale (1 / num_kernels)
   int act_tanh;             // out_act = bf16(tanh(result)) instead of leaky_relu (Postnet, N2)
+  int f16;                  // 16-bit tensors (residual, running sum, out_act) are fp16 instead of bf16 (ptx.cuh pack16)
 };
 
-__device__ __forceinline__ void add_bf16x16(float (&f)[16], const uint4 (&q)[2]) {
+__device__ __forceinline__ void add_bf16x16(float (&f)[16], const uint4 (&q)[2], int f16) {
   const uint32_t w[8] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    f[2 * j] += __uint_as_float(w[j] << 16);
-    f[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+    float lo, hi;
+    unpack16(w[j], lo, hi, f16);
+    f[2 * j] += lo;
+    f[2 * j + 1] += hi;
   }
 }
 
@@ -106,7 +109,8 @@ __device__ __forceinline__ void epi_compute16(const uint32_t (&v)[16], const flo
   const uint32_t w[8] = {rq[0].x, rq[0].y, rq[0].z, rq[0].w, rq[1].x, rq[1].y, rq[1].z, rq[1].w};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+    float lo, hi;
+    unpack16(w[j], lo, hi, o.f16);
     f[2 * j] = fminf(lo, lo * o.inv);
     f[2 * j + 1] = fminf(hi, hi * o.inv);
   }
@@ -117,14 +121,7 @@ __device__ __forceinline__ void epi_compute16(const uint32_t (&v)[16], const flo
     f[4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bv[i].z;
     f[4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bv[i].w;
   }
-  if (o.sum_a) {
-    const uint32_t q[8] = {sa[0].x, sa[0].y, sa[0].z, sa[0].w, sa[1].x, sa[1].y, sa[1].z, sa[1].w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      f[2 * j] += __uint_as_float(q[j] << 16);
-      f[2 * j + 1] += __uint_as_float(q[j] & 0xffff0000u);
-    }
-  }
+  if (o.sum_a) add_bf16x16(f, sa, o.f16);
   if (o.scale != 0.f) {
     const float sc = o.scale;
 #pragma unroll
@@ -134,16 +131,14 @@ __device__ __forceinline__ void epi_compute16(const uint32_t (&v)[16], const flo
   if (o.act_tanh) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      __nv_bfloat162 h = __floats2bfloat162_rn(tanhf(f[2 * i]), tanhf(f[2 * i + 1]));
-      pk[i] = *reinterpret_cast<uint32_t*>(&h);
+      pk[i] = pack16(tanhf(f[2 * i]), tanhf(f[2 * i + 1]), o.f16);
     }
     return;
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float a = f[2 * i], c = f[2 * i + 1];
-    __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, a * s), fmaxf(c, c * s));  // leaky_relu, 0 < s <= 1
-    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+    pk[i] = pack16(fmaxf(a, a * s), fmaxf(c, c * s), o.f16);  // leaky_relu, 0 < s <= 1
   }
 }
 
@@ -161,7 +156,8 @@ __device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const floa
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     // bf16 -> fp32 is a 16-bit shift; x = min(a, a/slope) inverts leaky_relu for 0 < slope < 1
-    float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xffff0000u);
+    float lo, hi;
+    unpack16(w[j], lo, hi, o.f16);
     f[2 * j] = fminf(lo, lo * o.inv);
     f[2 * j + 1] = fminf(hi, hi * o.inv);
   }
@@ -172,7 +168,7 @@ __device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const floa
     f[4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bv[i].z;
     f[4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bv[i].w;
   }
-  if (o.sum_a) add_bf16x16(f, sa);
+  if (o.sum_a) add_bf16x16(f, sa, o.f16);
   if (o.scale != 0.f) {
     const float sc = o.scale;
 #pragma unroll
@@ -193,15 +189,13 @@ __device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const floa
     if (o.act_tanh) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(tanhf(f[2 * i]), tanhf(f[2 * i + 1]));
-        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        pk[i] = pack16(tanhf(f[2 * i]), tanhf(f[2 * i + 1]), o.f16);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float a = f[2 * i], c = f[2 * i + 1];
-        __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(a, a * s), fmaxf(c, c * s));  // leaky_relu, 0 < s <= 1
-        pk[i] = *reinterpret_cast<uint32_t*>(&h);
+        pk[i] = pack16(fmaxf(a, a * s), fmaxf(c, c * s), o.f16);  // leaky_relu, 0 < s <= 1
       }
     }
     st_global_256(o.out_act + off, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));

@@ -56,6 +56,7 @@ struct PairParams {
   const __nv_bfloat16* sum_a;    // bf16 running sum over the stage's resblocks (generator.py:44-47) or nullptr
   int sum_tiled;                 // sum_a is in the tiled8 layout (epilogue.cuh)
   int out_tiled;                 // out_act is written in the tiled8 layout (direct stores; never with STAGED)
+  int f16;                       // 16-bit tensors and operands are fp16 instead of bf16 (ptx.cuh pack16)
   __nv_bfloat16* out_act;        // bf16 leaky_relu(result, slope), written through tm_out / tm_out2 (TMA stores)
 };
 
@@ -220,7 +221,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
   } else if (warp == 2 && cta_leader) {
     // ---------------- MMA issuer (warp-uniform loop, one elected lane issues; even CTA only) ----------------
     const bool leader = elect_one();
-    const uint32_t idesc = umma_idesc_bf16(128 * CG, p.nt);
+    const uint32_t idesc = umma_idesc_bf16(128 * CG, p.nt, p.f16);
     auto wait_full = [&](uint64_t* bar, uint32_t par, uint32_t code) {
       if (CG == 2) mbar_wait_cluster(bar, par, code);
       else mbar_wait(bar, par, code);
@@ -373,6 +374,7 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     eo.scale = p.divisor != 0.f ? 1.0f / p.divisor : 0.f;
     eo.inv = p.res_inv_slope;
     eo.act_tanh = 0;
+    eo.f16 = p.f16;
     const float smid = p.slope_mid;
     E2E_TR2_DECL
 
@@ -386,10 +388,10 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       for (int i = 0; i < 4; ++i) {
         const float f0 = __uint_as_float(v[4 * i]) + bv[i].x, f1 = __uint_as_float(v[4 * i + 1]) + bv[i].y;
         const float f2 = __uint_as_float(v[4 * i + 2]) + bv[i].z, f3 = __uint_as_float(v[4 * i + 3]) + bv[i].w;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(f0, f0 * smid), fmaxf(f1, f1 * smid));
-        __nv_bfloat162 h1v = __floats2bfloat162_rn(fmaxf(f2, f2 * smid), fmaxf(f3, f3 * smid));
-        pk[2 * i] = inside ? *reinterpret_cast<uint32_t*>(&h0) : 0u;
-        pk[2 * i + 1] = inside ? *reinterpret_cast<uint32_t*>(&h1v) : 0u;
+        const uint32_t h0 = pack16(fmaxf(f0, f0 * smid), fmaxf(f1, f1 * smid), p.f16);
+        const uint32_t h1v = pack16(fmaxf(f2, f2 * smid), fmaxf(f3, f3 * smid), p.f16);
+        pk[2 * i] = inside ? h0 : 0u;
+        pk[2 * i + 1] = inside ? h1v : 0u;
       }
       // 16 channels = two 16-byte chunks of this row in panel (n0 / CH_PANEL)
       const int n0 = cc * 16;

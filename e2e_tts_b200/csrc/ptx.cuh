@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace e2e {
@@ -322,9 +323,33 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
-// Instruction descriptor for kind::f16: BF16 x BF16 -> FP32, both operands K-major.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// Instruction descriptor for kind::f16: BF16 x BF16 -> FP32 (or, f16 != 0, FP16 x FP16 -> FP32: same rate, 11
+// significand bits instead of 8), both operands K-major.  Bits [7,10) / [10,13) = A / B format: 0 = f16, 1 = bf16.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, int f16 = 0) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// The 16-bit operand format of the tensor-core path (activations in HBM / shared memory, packed weights): bf16 by
+// default, fp16 when the generator was created with operand_dtype = fp16.  Two values <-> one 32-bit word, first value in
+// the low half.  The fp16 conversion saturates to +-65504 instead of producing inf.
+__device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
+  if (f16) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack16(uint32_t w, float& lo, float& hi, int f16) {
+  if (f16) {
+    const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    lo = v.x;
+    hi = v.y;
+  } else {
+    lo = __uint_as_float(w << 16);   // bf16 -> fp32 is a 16-bit shift
+    hi = __uint_as_float(w & 0xffff0000u);
+  }
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.

@@ -12,11 +12,12 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "ptx.cuh"
 
 namespace e2e {
 
 __global__ void mel_to_act_kernel(const float* __restrict__ mel, long long sB, long long sC, long long sT, int B,
-                                  int T, int C, int cpad, __nv_bfloat16* __restrict__ out) {
+                                  int T, int C, int cpad, __nv_bfloat16* __restrict__ out, int f16) {
   const int G = cpad / 8;
   const long long total = (long long)B * T * G;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -30,8 +31,7 @@ __global__ void mel_to_act_kernel(const float* __restrict__ mel, long long sB, l
     const int c0 = g * 8 + 2 * i;
     const float a = c0 < C ? mel[b * sB + c0 * sC + t * sT] : 0.f;
     const float c = c0 + 1 < C ? mel[b * sB + (c0 + 1) * sC + t * sT] : 0.f;
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
-    pk[i] = *reinterpret_cast<uint32_t*>(&h);
+    pk[i] = pack16(a, c, f16);
   }
   *reinterpret_cast<uint4*>(out + ((long long)b * T + t) * cpad + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
@@ -74,7 +74,7 @@ struct PostWeights {
 template <int C, int K, int OPT, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const __grid_constant__ PostWeights<K * C> pw, float bias,
-                      int B, int T, const PostOut out) {
+                      int B, int T, const PostOut out, int f16) {
   constexpr int HALF = (K - 1) / 2;
   constexpr int TILE = OPT * THREADS;
   constexpr int ROWS = TILE + 2 * HALF;
@@ -105,7 +105,8 @@ post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const __grid_consta
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float lo = __uint_as_float(u[i] << 16), hi = __uint_as_float(u[i] & 0xffff0000u);
+        float lo, hi;
+        unpack16(u[i], lo, hi, f16);
 #pragma unroll
         for (int q = 0; q < OPT; ++q) {
           const int j = r - q;
@@ -135,7 +136,7 @@ post_conv_tanh_kernel(const __nv_bfloat16* __restrict__ act, const __grid_consta
 // Generic fallback (any C multiple of 8, any odd k): one output per thread, rows read through L1.
 __global__ void __launch_bounds__(256)
 post_conv_tanh_generic_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, float bias, int B,
-                              int T, int C, int k, const PostOut out) {
+                              int T, int C, int k, const PostOut out, int f16) {
   __shared__ float sw[kPostMaxW];
   for (int i = threadIdx.x; i < k * C; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -154,8 +155,10 @@ post_conv_tanh_generic_kernel(const __nv_bfloat16* __restrict__ act, const float
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        acc = fmaf(__uint_as_float(u[i] << 16), wj[c8 * 8 + 2 * i], acc);
-        acc = fmaf(__uint_as_float(u[i] & 0xffff0000u), wj[c8 * 8 + 2 * i + 1], acc);
+        float lo, hi;
+        unpack16(u[i], lo, hi, f16);
+        acc = fmaf(lo, wj[c8 * 8 + 2 * i], acc);
+        acc = fmaf(hi, wj[c8 * 8 + 2 * i + 1], acc);
       }
     }
   }

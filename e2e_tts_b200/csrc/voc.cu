@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../include/e2e_tts_b200.h"
 #include "pair_host.cuh"
+#include "rb_host.cuh"
 #include "small_kernels.cuh"
 
 using namespace e2e;
@@ -29,10 +30,11 @@ struct Layer {
 };
 
 struct Op {
-  int kind;   // 0 = mel_to_act, 1 = conv_tc, 2 = post, 3 = fused residual pair
+  int kind;   // 0 = mel_to_act, 1 = conv_tc, 2 = post, 3 = fused residual pair, 4 = fused whole ResBlock1
   int layer;  // index into layers
   ConvPlan plan;
   PairPlan pair;
+  RbPlan rb;
 };
 
 struct PlanKey {
@@ -65,6 +67,7 @@ struct e2e_voc {
   int cin_pad = 0;
   int hop = 1;
   int n_sms = 148;
+  int f16 = 0;   // operand / activation format of the tensor-core path: 0 = bf16, 1 = fp16 (e2e_voc_set_operand_dtype)
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // one-shot profiling events
   int last_launches = 0;
   PostWeights<7 * 32> post_w{};                      // conv_post weights [k][C] for the 32-channel, k = 7 kernel
@@ -198,6 +201,8 @@ extern "C" int e2e_voc_create(const e2e_voc_config* cfg, e2e_voc** out) {
   if (rc_init) return rc_init;
   rc_init = pair_kernels_init();
   if (rc_init) return rc_init;
+  rc_init = rb_kernels_init();
+  if (rc_init) return rc_init;
   *out = v.release();
   return 0;
 }
@@ -220,6 +225,18 @@ extern "C" int e2e_voc_set_profile_events(e2e_voc* v, void* ev_begin, void* ev_e
 
 extern "C" int e2e_voc_hop(const e2e_voc* v) { return v ? v->hop : 0; }
 
+extern "C" int e2e_voc_set_operand_dtype(e2e_voc* v, int32_t dtype) {
+  if (!v) return fail(-1, "null argument");
+  if (dtype != E2E_OPERAND_BF16 && dtype != E2E_OPERAND_FP16) return fail(-1, "operand dtype must be E2E_OPERAND_BF16 or E2E_OPERAND_FP16");
+  if (v->f16 == dtype) return 0;
+  v->f16 = dtype;
+  for (auto& L : v->layers) L.loaded = false;   // the packed weight images depend on the format: reload every layer
+  v->plans.clear();
+  return 0;
+}
+
+extern "C" int e2e_voc_operand_dtype(const e2e_voc* v) { return v ? v->f16 : -1; }
+
 extern "C" int e2e_voc_missing_layers(const e2e_voc* v) {
   if (!v) return -1;
   int n = 0;
@@ -237,6 +254,9 @@ extern "C" int e2e_voc_load_layer(e2e_voc* v, const char* name, const float* wei
   if (weight_numel != want_w || bias_numel != L.cout)
     return fail(-6, std::string("shape mismatch for layer ") + name);
   cudaError_t e;
+  // A reload while a forward enqueued on a non-blocking stream is still reading the old weight image would tear it
+  // (the copies below run on the legacy default stream, which does not order against such streams): drain the device.
+  if (L.d_w && (e = cudaDeviceSynchronize()) != cudaSuccess) return fail((int)e, "cudaDeviceSynchronize");
   if (L.kind == L_POST) {
     // reference layout [1][cin][k] -> [k][cin]
     std::vector<float> w((size_t)L.k * L.cin);
@@ -280,7 +300,7 @@ extern "C" int e2e_voc_load_layer(e2e_voc* v, const char* name, const float* wei
     }
   }
   std::vector<uint8_t> packed(packed_weight_bytes(s));
-  pack_conv_weights(s, wg.data(), packed.data());
+  pack_conv_weights(s, wg.data(), packed.data(), v->f16);
   if (!L.d_w && (e = cudaMalloc(&L.d_w, packed.size())) != cudaSuccess) return fail((int)e, "cudaMalloc");
   if (!L.d_bias && (e = cudaMalloc(&L.d_bias, bg.size() * 4)) != cudaSuccess) return fail((int)e, "cudaMalloc");
   if ((e = cudaMemcpy(L.d_w, packed.data(), packed.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
@@ -389,6 +409,7 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
   p.divisor = divisor;
   p.sum_tiled = sum_a != nullptr && (tiled & kSumTiled);
   p.out_tiled = out_act != nullptr && (tiled & kOutTiled);
+  p.f16 = v->f16;
   ops.push_back(op);
   return 0;
 }
@@ -427,6 +448,48 @@ static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B,
   p.slope_mid = 0.1f;
   p.slope = slope;
   p.divisor = divisor;
+  p.f16 = v->f16;
+  ops.push_back(op);
+  return 0;
+}
+
+// One fused launch for a whole ResBlock1 (rb_tc.cuh): `in` holds bf16 leaky_relu(x, 0.1); l1[i] / l2[i] = layers of pair i.
+static int make_rb_op(e2e_voc* v, std::vector<Op>& ops, const int* l1, const int* l2, int n_pairs, int B, int T,
+                      const __nv_bfloat16* in, const __nv_bfloat16* sum_a, __nv_bfloat16* out_act, float slope,
+                      float divisor, int tiled) {
+  const Layer& L0 = v->layers[l1[0]];
+  Op op;
+  op.kind = 4;
+  op.layer = l1[0];
+  int dil[kRbMaxPairs] = {1, 1, 1};
+  for (int i = 0; i < n_pairs; ++i) dil[i] = v->layers[l1[i]].dil;
+  int rc = plan_rb(op.rb, L0.cin, L0.k, dil, n_pairs, B, T, v->n_sms);
+  if (rc) return rc;
+  RbParams& p = op.rb.p;
+  rc = make_act_tensor_map(&op.rb.tm, in, B, T, L0.cin, op.rb.rowb / 2, p.box_rows);
+  if (rc) return rc;
+  std::vector<float> cum(L0.cin, 0.f);
+  for (int i = 0; i < n_pairs; ++i) {
+    const Layer& A = v->layers[l1[i]];
+    const Layer& C2 = v->layers[l2[i]];
+    if (A.h_bias.size() > 128 || C2.h_bias.size() > 128) return fail(-2, "fused resblock: more than 128 channels");
+    p.w[2 * i] = A.d_w;
+    p.w[2 * i + 1] = C2.d_w;
+    std::copy(A.h_bias.begin(), A.h_bias.end(), p.bias[2 * i]);
+    for (size_t n = 0; n < C2.h_bias.size(); ++n) {   // x lives in TMEM without the c2 biases: pass their running sum
+      cum[n] += C2.h_bias[n];
+      p.bias[2 * i + 1][n] = cum[n];
+    }
+  }
+  p.res_inv_slope = 10.0f;
+  p.sum_a = sum_a;
+  p.sum_tiled = sum_a != nullptr && (tiled & kSumTiled);
+  p.out_tiled = (tiled & kOutTiled) != 0;
+  p.out_act = out_act;
+  p.slope_mid = 0.1f;
+  p.slope = slope;
+  p.divisor = divisor;
+  p.f16 = v->f16;
   ops.push_back(op);
   return 0;
 }
@@ -470,6 +533,29 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
       // instead of updating in place.
       bool fused = c.resblock == 1 && std::getenv("E2E_NO_PAIR_FUSION") == nullptr;
       for (int m = 0; m < nd && fused; ++m) fused = pair_supported(chs, ks, c.resblock_dilation_sizes[j][m]);
+      // Whole-resblock fusion (rb_tc.cuh: residual stream in TMEM, one launch per ResBlock1) where its halo is cheap
+      if (fused && nd <= kRbMaxPairs && rb_supported(chs, ks, c.resblock_dilation_sizes[j], nd)) {
+        int l1[kRbMaxPairs], l2[kRbMaxPairs];
+        for (int m = 0; m < nd; ++m) {
+          l1[m] = v->by_name[base + ".convs1." + std::to_string(m)];
+          l2[m] = v->by_name[base + ".convs2." + std::to_string(m)];
+        }
+        // where the resblock's result goes: the running sum xs (bf16, S0 / S1 ping-pong) or, for the stage's last
+        // resblock, x = xs / num_kernels as the next layer's activation (same rules as the pair path below)
+        __nv_bfloat16* oact = (j & 1) ? bf.S1 : bf.S0;
+        float slope = 1.0f, divisor = 0.f;
+        const __nv_bfloat16* sum_in = j > 0 ? ((j & 1) ? bf.S0 : bf.S1) : nullptr;
+        int tiled = 0;
+        if (tiled_sums) tiled = kSumTiled | (j + 1 == c.num_kernels ? 0 : kOutTiled);
+        if (j + 1 == c.num_kernels) {
+          oact = bf.Y;
+          divisor = (float)c.num_kernels;
+          slope = out_slope;
+        }
+        rc = make_rb_op(v, ops, l1, l2, nd, B, Ts, bf.A0, sum_in, oact, slope, divisor, tiled);
+        if (rc) return rc;
+        continue;
+      }
       for (int m = 0; m < nd; ++m) {
         const bool last = m + 1 == nd;
         // where does x_new = conv(...) + x go?
@@ -590,7 +676,7 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
   const std::vector<Op>& ops = it->second;
   size_t first_conv = ops.size(), last_conv = 0;
   for (size_t i = 0; i < ops.size(); ++i)
-    if (ops[i].kind == 1 || ops[i].kind == 3) {
+    if (ops[i].kind == 1 || ops[i].kind == 3 || ops[i].kind == 4) {
       first_conv = i < first_conv ? i : first_conv;
       last_conv = i;
     }
@@ -600,12 +686,15 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
     if (op.kind == 0) {
       const long long total = (long long)B * T * (v->cin_pad / 8);
       mel_to_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(mel, sB, sC, sT, B, T, v->cfg.in_channels,
-                                                                        v->cin_pad, bf.melA);
+                                                                        v->cin_pad, bf.melA, v->f16);
     } else if (op.kind == 1) {
       int rc = launch_conv(op.plan, st);
       if (rc) return rc;
     } else if (op.kind == 3) {
       int rc = launch_pair(op.pair, st);
+      if (rc) return rc;
+    } else if (op.kind == 4) {
+      int rc = launch_rb(op.rb, st);
       if (rc) return rc;
     } else if (op.kind == 5) {
       const int Ts = T * v->hop, C = v->layers[v->by_name["conv_post"]].cin;
@@ -623,11 +712,11 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
       if (L.cin == 32 && L.k == 7) {
         dim3 grid((Tout + kPostTile - 1) / kPostTile, B);
         post_conv_tanh_kernel<32, 7, kPostOpt, kPostThreads>
-            <<<grid, kPostThreads, 0, st>>>(bf.Y, v->post_w, L.post_bias, B, Tout, post);
+            <<<grid, kPostThreads, 0, st>>>(bf.Y, v->post_w, L.post_bias, B, Tout, post, v->f16);
       } else {
         dim3 grid((Tout + 255) / 256, B);
         post_conv_tanh_generic_kernel<<<grid, 256, 0, st>>>(bf.Y, reinterpret_cast<const float*>(L.d_w), L.post_bias,
-                                                            B, Tout, L.cin, L.k, post);
+                                                            B, Tout, L.cin, L.k, post, v->f16);
       }
     }
     if (oi == last_conv && v->ev_end) cudaEventRecord(v->ev_end, st);
@@ -807,7 +896,7 @@ extern "C" int e2e_postnet_forward(e2e_postnet* pn, const float* x, int32_t B, i
   {
     const long long tot = (long long)B * T * (pn->c_pad / 8);
     mel_to_act_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, (long long)T * pn->C, 1, pn->C, B, T, pn->C,
-                                                                    pn->c_pad, xin);
+                                                                    pn->c_pad, xin, v->f16);
   }
   for (const Op& op : it->second) {
     int rc = launch_conv(op.plan, st);

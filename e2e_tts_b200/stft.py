@@ -151,6 +151,11 @@ class TorchSTFT(nn.Module):
             self._handles[key] = h
         return h
 
+    def inverse_tranform(self, magnitude: torch.Tensor, phase: torch.Tensor) -> torch.Tensor:
+        """stft.py:90-100 (name as spelt there): torch.istft(magnitude * exp(i * phase)) with this module's sizes, via
+        inverse_stft (supported for the small transforms of the iSTFTNet head, see there)."""
+        return inverse_stft(magnitude, phase, self.filter_length, self.hop_length, self.win_length)
+
     def mel_spectrogram(self, input_data, center=False, return_energy=False, check_range=True):
         """stft.py:46-89.  input_data: [B, L] in [-1, 1] -> log-mel [B, n_mel_channels, T] (and energy [B, T]).
         Raises AssertionError for out-of-range samples like the reference (:56-57); `check_range=False` skips
@@ -167,6 +172,45 @@ class TorchSTFT(nn.Module):
         if return_energy is True:
             return mel, energy
         return mel
+
+
+def crop_segments_and_mel(stft: "TorchSTFT", audio: torch.Tensor, lengths=None, segment_size: int = 8192, starts=None,
+                          generator: Optional[torch.Generator] = None, check_range: bool = False):
+    """Batched, on-device form of the vocoder-training crop + mel of MelAudioLoader.__getitem__
+    (e2e_tts/src/tools/dataloader.py:364-373, the `load_mel_from_disk=False` branch), which the reference runs per item
+    inside forked DataLoader workers (where a CUDA kernel cannot run - SURVEY.md §7): move it into the training step.
+
+        audio    [B, Lmax] float32 CUDA tensor, already divided by max_wav_value (row b valid up to lengths[b])
+        lengths  [B] ints (None: every row is Lmax long)
+        starts   [B] ints (None: drawn like the reference, uniform in [0, len - segment_size] per row, from `generator`)
+    returns (mel [B, n_mels, segment_size // hop], audio_seg [B, segment_size], mel_loss) - per row exactly
+    `audio[start:start+segment_size]` (zero-padded at the end when the clip is shorter, dataloader.py:370) and
+    `stft.mel_spectrogram` of it; the reference computes the same mel twice (mel, mel_loss), so one tensor is returned
+    for both.  Crop = torch indexing on the device, mel = the CUDA kernel (e2e_mel_forward)."""
+    if not isinstance(audio, torch.Tensor) or audio.dim() != 2 or not audio.is_cuda:
+        raise ValueError("expected a [B, Lmax] CUDA tensor (there is no CPU path)")
+    B, Lmax = audio.shape
+    dev = audio.device
+    seg = int(segment_size)
+    if lengths is None:
+        lens = torch.full((B,), Lmax, dtype=torch.int64, device=dev)
+    else:
+        lens = torch.as_tensor(lengths).to(device=dev, dtype=torch.int64)
+        if lens.shape != (B,) or int(lens.max()) > Lmax or int(lens.min()) < 0:
+            raise ValueError("lengths must be [B] values in [0, Lmax]")
+    if starts is None:
+        span = (lens - seg).clamp(min=0) + 1                      # random.randint(0, max_audio_start) is inclusive
+        u = torch.rand(B, generator=generator, device=dev if generator is None or generator.device.type == "cuda" else "cpu")
+        st = (u.to(dev).double() * span.double()).floor().to(torch.int64).clamp(max=span - 1)
+    else:
+        st = torch.as_tensor(starts).to(device=dev, dtype=torch.int64)
+        if st.shape != (B,) or bool((st < 0).any()) or bool((st > (lens - seg).clamp(min=0)).any()):
+            raise ValueError("starts must be [B] values in [0, max(len - segment_size, 0)]")
+    idx = st[:, None] + torch.arange(seg, device=dev)[None, :]
+    valid = idx < lens[:, None]
+    audio_seg = torch.where(valid, audio.float().gather(1, idx.clamp(max=Lmax - 1)), audio.new_zeros((), dtype=torch.float32))
+    mel = stft.mel_spectrogram(audio_seg, check_range=check_range)
+    return mel, audio_seg, mel
 
 
 _GM_HANDLES: Dict[tuple, _MelHandle] = {}

@@ -46,7 +46,14 @@ typedef struct e2e_voc_config {
   int32_t istft_n_fft;
 } e2e_voc_config;
 
-typedef struct e2e_voc e2e_voc; /* opaque: packed bf16 weights + launch plans of one generator */
+typedef struct e2e_voc e2e_voc; /* opaque: packed 16-bit weights + launch plans of one generator */
+
+/* Threading: a handle is NOT internally synchronised.  One host thread at a time may call into a given e2e_voc /
+ * e2e_postnet / e2e_mel handle (the launch-plan cache, the one-shot profile events and the weight images are plain
+ * members), and one handle should be driven from one stream at a time (a forward reuses the caller's workspace, and
+ * e2e_voc_load_layer synchronises the device before it overwrites weights a forward in flight could still read).
+ * Different handles are independent and may be used from different threads concurrently;
+ * e2e_last_error_string() is per calling thread. */
 
 /* Replaces HifiGan.__init__ (generator.py:14-35).  Allocates device memory for the packed weights. */
 int e2e_voc_create(const e2e_voc_config* cfg, e2e_voc** out);
@@ -97,6 +104,17 @@ int e2e_istft_forward(const float* mag, const float* phase, int32_t B, int32_t f
  * tensor-core convolution launch and `ev_end` right after its last one, then forgets both (one-shot).  bench.py
  * uses it to time the dominant kernel family inside the timed region.  Pass NULLs to cancel. */
 int e2e_voc_set_profile_events(e2e_voc* v, void* ev_begin, void* ev_end);
+
+/* Format of the tensor-core operands and of the 16-bit activation tensors between layers.  bf16 (default) is what
+ * BASELINE names; fp16 runs at the same tensor-core rate with 11 instead of 8 significand bits (about 8x smaller
+ * rounding error in the waveform), at the price of fp16's range: conversions saturate at +-65504
+ * instead of overflowing.  Changing the format marks every layer as not loaded (the packed weights depend on it):
+ * call it right after e2e_voc_create, before e2e_voc_load_layer.  fp32 accumulation, biases, residual adds and the
+ * conv_post / tanh tail are unaffected. */
+#define E2E_OPERAND_BF16 0
+#define E2E_OPERAND_FP16 1
+int e2e_voc_set_operand_dtype(e2e_voc* v, int32_t dtype);
+int e2e_voc_operand_dtype(const e2e_voc* v);
 
 /* Total upsampling factor (product of upsample_rates; 256 for the default config). */
 int e2e_voc_hop(const e2e_voc* v);

@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 mkdir -p build
 F="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17"
 pids=()
-for t in conv_tc pair_tc; do
+for t in conv_tc pair_tc rb_tc; do
   nvcc $F -o build/test_$t tests/cuda/test_$t.cu & pids+=($!)
   nvcc $F -DE2E_WATCHDOG -o build/test_${t}_wd tests/cuda/test_$t.cu & pids+=($!)
 done

@@ -23,10 +23,15 @@ import margins
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-MAX_TOL, MEAN_TOL = 2e-2, 3e-3
+# bf16 operands: max |err| <= 2 % of the utterance's abs-max.  The MEAN bound at full size is 3.5e-3
+# instead of c6's provisional 3e-3 ("to be confirmed on hardware"): scripts/emulate_numerics.py shows that ANY
+# implementation with bf16 tensor-core operands lands at 0.21-0.26 % mean / 1.3 % max on these seeds (operand rounding
+# alone, everything else fp32; profiles/r02_numerics_emulation.txt), the kernels' extra bf16 storage points add 0.04-0.07 %.
+# operand_dtype="fp16" (same speed) is held to bounds 5x tighter, see test_gpu_vocoder.py.
+MAX_TOL, MEAN_TOL = 2e-2, 3.5e-3
 
 
-def check_against_full_golden(name, wav):
+def check_against_full_golden(name, wav, max_tol=MAX_TOL, mean_tol=MEAN_TOL, tag=""):
     """Every utterance of the batch vs the reference's strided waveform sample."""
     g = np.load(os.path.join(GOLD, name + ".npz"))
     idx = torch.from_numpy(g["index"])
@@ -37,13 +42,13 @@ def check_against_full_golden(name, wav):
     for b in range(ref.shape[0]):
         scale = ref[b].abs().max().item()
         d = (got[b] - ref[b]).abs()
-        margins.record("%s utterance %d" % (name, b), max_rel=d.max().item() / scale, mean_rel=d.mean().item() / scale,
-                       bound_max=MAX_TOL, bound_mean=MEAN_TOL, scale=scale)
-        assert d.max().item() <= MAX_TOL * scale, "%s utterance %d: max err %.3g vs scale %.3g" % (name, b, d.max().item(), scale)
-        assert d.mean().item() <= MEAN_TOL * scale, "%s utterance %d: mean err %.3g" % (name, b, d.mean().item())
+        margins.record("%s%s utterance %d" % (tag, name, b), max_rel=d.max().item() / scale,
+                       mean_rel=d.mean().item() / scale, bound_max=max_tol, bound_mean=mean_tol, scale=scale)
+        assert d.max().item() <= max_tol * scale, "%s utterance %d: max err %.3g vs scale %.3g" % (name, b, d.max().item(), scale)
+        assert d.mean().item() <= mean_tol * scale, "%s utterance %d: mean err %.3g" % (name, b, d.mean().item())
         edge = 2048   # the first / last 2048 entries are the utterance ends (per-layer zero padding)
         for sl in (slice(0, edge), slice(-edge, None)):
-            assert d[sl].max().item() <= MAX_TOL * scale
+            assert d[sl].max().item() <= max_tol * scale
         worst = max(worst, d.max().item() / scale)
     return worst
 
@@ -53,9 +58,9 @@ def mel_like(B, T, seed):
     return (torch.randn(B, 80, T, generator=g) * 2.0 - 5.0).clamp(-11.5, 2.0)
 
 
-def build(seed):
+def build(seed, operand_dtype=None):
     sd = ho.make_state_dict(ho.DEFAULT_CONFIG, seed, "strong")
-    voc = pkg.HifiGan(ho.DEFAULT_CONFIG)
+    voc = pkg.HifiGan(ho.DEFAULT_CONFIG, operand_dtype=operand_dtype)
     voc.load_state_dict(sd)
     return voc.eval().to("cuda"), sd
 
@@ -79,6 +84,15 @@ def test_cfg2_batch16_x_5s_properties():
     g = np.load(os.path.join(GOLD, "full_cfg2.npz"))
     assert int(g["weight_seed"]) == 21 and int(g["mel_seed"]) == 31 and int(g["B"]) == B and int(g["T"]) == T
     check_against_full_golden("full_cfg2", a)
+
+
+@pytest.mark.parametrize("name,B,T,wseed,mseed", [("full_cfg2", 16, 431, 21, 31), ("full_cfg3", 8, 2584, 22, 32)])
+def test_full_size_fp16_operands_every_utterance(name, B, T, wseed, mseed):
+    """operand_dtype="fp16" at BASELINE's full sizes: every utterance within max 4e-3 / mean 6e-4 of the reference."""
+    voc, _ = build(wseed, operand_dtype="fp16")
+    with torch.no_grad():
+        a = voc(mel_like(B, T, mseed).cuda())
+    check_against_full_golden(name, a, 4e-3, 6e-4, tag="fp16 ")
 
 
 def test_cfg3_batch8_x_30s_rows_match_single_runs():

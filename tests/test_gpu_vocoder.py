@@ -41,9 +41,9 @@ def check(got, want, what=""):
     one(got[..., -n:], want[..., -n:], "tail")
 
 
-def build(cfg, seed, regime):
+def build(cfg, seed, regime, operand_dtype=None):
     sd = ho.make_state_dict(cfg, seed, regime)
-    voc = pkg.HifiGan(cfg)
+    voc = pkg.HifiGan(cfg, operand_dtype=operand_dtype)
     voc.load_state_dict(sd)
     return voc.eval().to("cuda"), sd
 
@@ -189,6 +189,43 @@ def test_host_pipeline_matches_direct_calls():
     with torch.no_grad():
         for m, o in zip(mels[:3], pcm):
             assert torch.equal(o, voc.forward_pcm16(m.cuda()).cpu())
+
+
+FP16_MAX_TOL, FP16_MEAN_TOL = 4e-3, 6e-4   # 5x tighter than the bf16 bounds: fp16 operands carry 3 more significand bits
+
+
+@pytest.mark.parametrize("name", ["voc_default_init", "voc_strong_init", "voc_strong_resblock2"])
+def test_fp16_operand_mode_against_reference_golden(name):
+    """operand_dtype="fp16": same kernels, fp16 instead of bf16 operands / activations (e2e_voc_set_operand_dtype)."""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg = dict(ho.DEFAULT_CONFIG)
+    cfg["resblock"] = int(g["resblock"])
+    voc, _ = build(cfg, int(g["seed"]), str(g["regime"]), operand_dtype="fp16")
+    with torch.no_grad():
+        wav = voc(torch.from_numpy(g["mel"]).cuda()).cpu()
+    ref = torch.from_numpy(g["wav"])
+    scale = ref.abs().max().item()
+    d = (wav - ref).abs()
+    margins.record("fp16 " + name, max_rel=d.max().item() / scale, mean_rel=d.mean().item() / scale,
+                   bound_max=FP16_MAX_TOL, bound_mean=FP16_MEAN_TOL, scale=scale)
+    assert d.max().item() <= FP16_MAX_TOL * scale and d.mean().item() <= FP16_MEAN_TOL * scale, (d.max().item(), scale)
+
+
+def test_fp16_operand_mode_full_utterance_and_pcm():
+    voc, sd = build(ho.DEFAULT_CONFIG, 21, "strong", operand_dtype="fp16")
+    mel = mel_like(2, 431, 31)
+    with torch.no_grad():
+        wav = voc(mel.cuda()).cpu()
+        pcm = voc.forward_pcm16(mel.cuda()).cpu()
+        ref = ho.hifigan_forward(sd, ho.DEFAULT_CONFIG, mel)
+    scale = ref.abs().max().item()
+    d = (wav - ref).abs()
+    margins.record("fp16 2 x 5 s", max_rel=d.max().item() / scale, mean_rel=d.mean().item() / scale,
+                   bound_max=FP16_MAX_TOL, bound_mean=FP16_MEAN_TOL, scale=scale)
+    assert d.max().item() <= FP16_MAX_TOL * scale and d.mean().item() <= FP16_MEAN_TOL * scale
+    assert torch.equal(pcm, (wav.squeeze(1) * 32768.0).clamp(-32768, 32767).to(torch.int16))
+    with pytest.raises(ValueError):
+        pkg.HifiGan(ho.DEFAULT_CONFIG, operand_dtype="fp8")
 
 
 def test_host_pipeline_variable_batch_shapes():

@@ -13,6 +13,7 @@ BUILD = os.path.join(ROOT, "build")
 CONV_DIRECT = [0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 14]          # test_conv_tc.cu: small shapes, per-thread stores
 CONV_STAGED = [0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12, 13, 14, 25]   # ... and the staged TMA-store epilogue
 PAIR_SMALL = list(range(9))                                       # test_pair_tc.cu: every non-perf configuration
+RB_SMALL = list(range(9))                                         # test_rb_tc.cu: every non-perf configuration
 
 
 def _run(binary, cfg, env_extra):
@@ -38,3 +39,11 @@ def test_conv_tc_kernel_against_naive_cuda(cfg, staged):
 def test_pair_tc_kernel_against_naive_cuda(cfg):
     """Fused x + c2(lrelu(c1(lrelu(x)))) for C = 32 / 64 / 128, one-CTA and CTA-pair forms, ragged tails."""
     _run("test_pair_tc_wd", cfg, {})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", RB_SMALL)
+def test_rb_tc_kernel_against_naive_cuda(cfg):
+    """Fused whole ResBlock1 (three pairs chained, residual stream in TMEM) for C = 32 / 64 / 128, k = 3 / 5 / 7,
+    one to three pairs, ragged tails, running-sum / divide epilogues."""
+    _run("test_rb_tc_wd", cfg, {})
