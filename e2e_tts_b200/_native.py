@@ -51,6 +51,13 @@ SYMBOLS = {
     "e2e_voc_operand_dtype": (c_int, [c_void_p]),
     "e2e_voc_hop": (c_int, [c_void_p]),
     "e2e_voc_launches_per_forward": (c_int, [c_void_p]),
+    "e2e_voc_last_forward_was_graph": (c_int, [c_void_p]),
+    "e2e_resblock_create": (c_int, [c_int32, c_int32, c_int32, POINTER(c_int32), c_int32, POINTER(c_void_p)]),
+    "e2e_resblock_destroy": (None, [c_void_p]),
+    "e2e_resblock_load_layer": (c_int, [c_void_p, c_char_p, POINTER(c_float), c_int64, POINTER(c_float), c_int64]),
+    "e2e_resblock_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
+    "e2e_resblock_forward": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int32, c_int32, c_void_p,
+                                     c_void_p, c_size_t, c_void_p]),
     "e2e_postnet_create": (c_int, [c_int32, c_int32, c_int32, c_int32, POINTER(c_void_p)]),
     "e2e_postnet_destroy": (None, [c_void_p]),
     "e2e_postnet_load_layer": (c_int, [c_void_p, c_int32, POINTER(c_float), c_int64, POINTER(c_float), c_int64]),

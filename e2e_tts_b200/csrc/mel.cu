@@ -4,18 +4,21 @@
 //   reflect-pad 384 | frame t = xp[256 t .. +1024) * periodic Hann | 1024-pt real FFT | sqrt(re^2+im^2+1e-9)
 //   | sparse Slaney mel filterbank | log(max(., 1e-5)) | energy = sqrt(sum_k mag^2)
 //
-// The path is bandwidth-shaped (4 B in, 0.32 B out per sample) but a direct DFT would be ~2 MFLOP per frame,
-// so the transform is FFT-structured on chip: a CTA stages the audio of 32 consecutive frames in shared memory
-// once (frames overlap 4x), and each group of 64 threads runs a 512-point complex FFT of the even/odd-packed
-// frame as three radix-8 passes held in registers (8 complex values per thread), exchanging through padded,
-// conflict-free shared-memory maps, followed by the real-FFT recombination pass, which produces the bins k and
-// 512-k from one pair of loads (X[512-k] = conj(Ze - W^k Zo)) and only the bins the filterbank reads (0..371 for
-// fmax = 8 kHz).  The frame energy sqrt(sum_k mag_k^2) over all 513 bins comes from Parseval's identity on the
-// windowed samples: sum_{k<=512} |X_k|^2 = (1024 sum_n xw_n^2 + X_0^2 + X_512^2) / 2 (shuffle-reduced).  The mel
-// filterbank is applied in its sparse, block form: thread t of a frame owns BPT consecutive bins and the (at most FPB)
-// triangular filters that overlap them, as a dense FPB x BPT block of weights - branch-free, conflict-free, and
-// deterministic (fixed-order partial sums per filter); outputs are staged so that the global stores of
-// mel[b][m][t0..t0+32) are 128-byte coalesced.  The index maps are emulated and
+// The path is bandwidth-shaped (4 B in, 0.32 B out per sample) but a direct DFT would be ~2 MFLOP per frame, so the
+// transform is FFT-structured on chip.  A CTA stages the audio of 32 consecutive frames in shared memory once (frames
+// overlap 4x); each group of 64 threads runs the 512-point complex FFT of an even/odd-packed frame as three radix-8
+// passes held in registers (8 complex values per thread, packed f32x2 arithmetic), exchanging through one padded,
+// conflict-free shared-memory buffer after passes 1 and 2.  What bounds the kernel is instruction issue (~700 instructions
+// per thread and frame in round 1: profiles/r02_mel_notes.md), so this version spends its changes on instruction count:
+//   * complex butterflies and twiddle multiplies in Blackwell's packed FP32 instructions (FADD2 / FMUL2 / FFMA2);
+//   * the real-FFT recombination pairs bin k with 512 - k.  With k = k1 + 8 c + 64 d held by thread (k1, c) in register d,
+//     512 - k lives in ONE other thread, (8 - k1, 7 - c) [(0, 8 - c) for k1 = 0], in register 7 - d: the k1 -> thread
+//     map is permuted so that both are in the same warp, and eight shuffles bring the partner's values;
+//   * the magnitudes of all 32 frames stay in shared memory ([frame][bin], odd pitch) and the mel filterbank runs once
+//     per CTA with frames on the lanes: for filter m a warp walks the filter's bins, the weight is warp-uniform (one
+//     broadcast read) and lane f reads mag[f][k] conflict-free; the log-mel leaves as a coalesced 128-byte row store.
+// The frame energy sqrt(sum_k mag_k^2) over all 513 bins comes from Parseval's identity on the windowed samples:
+// sum_{k<=512} |X_k|^2 = (1024 sum_n xw_n^2 + X_0^2 + X_512^2) / 2 (shuffle-reduced).  The index maps are emulated and
 // checked on the CPU in tests/test_mel_fft_plan.py.
 #include <cmath>
 #include <cstring>
@@ -32,28 +35,27 @@ constexpr int kNfft = 1024;
 constexpr int kHop = 256;
 constexpr int kPad = (kNfft - kHop) / 2;  // 384, stft.py:33
 constexpr int kBins = kNfft / 2 + 1;      // 513
-constexpr int kF = 32;                    // frames per CTA
+constexpr int kF = 32;                    // frames per CTA (= lanes of the filterbank pass)
 constexpr int kGroups = 4;                // 64-thread FFT groups per CTA
 constexpr int kThreads = kGroups * 64;
 constexpr int kAudio = (kF - 1) * kHop + kNfft;  // samples staged per CTA
-constexpr int kSx = 576;                  // padded complex exchange buffer (8 rows of 72 / 64 rows of 9)
-constexpr int kMagPad = 584;              // 64 blocks x pitch 9 (BPT = 8), multiple of 4
-constexpr int kFbSplitMax = 12;           // partial-sum slots per filter (a filter spans <= 12 threads' bin blocks)
+constexpr int kSx = 576;                  // padded complex exchange buffer (8 rows of 72)
+constexpr int kMaxMels = 128;
 
 struct MelParams {
   const float* wav;
   long long ldw, L;
-  int B, T, n_mels, nnz;
-  int nb;               // bins the filterbank reads: 1 + last non-zero column of the basis
-  int fb_split;         // partial-sum slots per filter = the most bin blocks any filter overlaps
+  int B, T, n_mels;
+  int nb;               // bins the filterbank reads: 1 + last non-zero column of the basis (<= 513)
+  int magp;             // odd row pitch of the magnitude tile (>= nb)
+  int n_w;              // packed filterbank weights
   float* mel;
   float* energy;
   int* range_flag;
   const float* window;  // [1024] periodic Hann
   const float2* tw;     // [1024] exp(-2 pi i j / 1024)
-  const float4* fb_w;   // [ceil(FPB*BPT/4)][64] weights of thread t's block: element j*BPT + i = basis[filter j][bin i]
-  const int* fb_slot;   // [FPB][64] where filter j of thread t leaves its partial sum: mel * fb_split + (index of the
-                        // thread among the filter's threads); unused j -> the scratch slot n_mels * fb_split
+  const float* fb_w;    // [n_w] filter m: weights of bins fb_lo[m] .. fb_lo[m] + fb_n[m] - 1 at fb_off[m] (zeros inside kept)
+  const int* fb_meta;   // [3][n_mels]: lo, n, off
 };
 
 __device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT: max relative error 2^-23 (PTX ISA)
@@ -62,65 +64,99 @@ __device__ __forceinline__ float sqrt_approx(float x) {  // MUFU.SQRT: max relat
   return y;
 }
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// Complex values travel as packed f32x2 register pairs (lo = re, hi = im) and the butterflies use Blackwell's packed
+// FP32 instructions (FADD2 / FMUL2 / FFMA2: one instruction per complex add, two per complex multiply) - the kernel
+// is bound by instruction issue, not by memory (profiles/r02_mel_notes.md).
+typedef unsigned long long c64;
+__device__ __forceinline__ c64 pk2(float lo, float hi) {
+  c64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
 }
-__device__ __forceinline__ float2 mul_neg_i(float2 a) { return make_float2(a.y, -a.x); }
+__device__ __forceinline__ void up2(c64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ c64 add2(c64 a, c64 b) {
+  c64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ c64 sub2(c64 a, c64 b) {
+  c64 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ c64 mul2(c64 a, c64 b) {
+  c64 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ c64 fma2(c64 a, c64 b, c64 c) {
+  c64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ c64 swap2(c64 a) {   // (re, im) -> (im, re): folds into the consumer's operand swizzle
+  float lo, hi;
+  up2(a, lo, hi);
+  return pk2(hi, lo);
+}
+// a * w for w = (wx, wy):  wx * a + (-wy, wy) * (a.im, a.re)
+__device__ __forceinline__ c64 cmul2(c64 a, float wx, float wy) {
+  return fma2(pk2(wx, wx), a, mul2(swap2(a), pk2(-wy, wy)));
+}
+// d + (-i) e = (d.re + e.im, d.im - e.re)   and   d - (-i) e
+__device__ __forceinline__ c64 add_negi(c64 d, c64 e) { return fma2(swap2(e), pk2(1.f, -1.f), d); }
+__device__ __forceinline__ c64 sub_negi(c64 d, c64 e) { return fma2(swap2(e), pk2(-1.f, 1.f), d); }
 
-__device__ __forceinline__ void dft4(float2 c0, float2 c1, float2 c2, float2 c3, float2& y0, float2& y1, float2& y2,
-                                     float2& y3) {
-  const float2 d0 = cadd(c0, c2), d2 = csub(c0, c2), d1 = cadd(c1, c3), d3 = mul_neg_i(csub(c1, c3));
-  y0 = cadd(d0, d1);
-  y1 = cadd(d2, d3);
-  y2 = csub(d0, d1);
-  y3 = csub(d2, d3);
+// 4-point DFT of (c0, c1, c2', c3) where c2' = -i * c2 when C2_NEGI (the W8^2 twiddle of dft8 folded into the adds)
+template <bool C2_NEGI>
+__device__ __forceinline__ void dft4(c64 c0, c64 c1, c64 c2, c64 c3, c64& y0, c64& y1, c64& y2, c64& y3) {
+  const c64 d0 = C2_NEGI ? add_negi(c0, c2) : add2(c0, c2);
+  const c64 d2 = C2_NEGI ? sub_negi(c0, c2) : sub2(c0, c2);
+  const c64 d1 = add2(c1, c3), e = sub2(c1, c3);
+  y0 = add2(d0, d1);
+  y2 = sub2(d0, d1);
+  y1 = add_negi(d2, e);
+  y3 = sub_negi(d2, e);
 }
 
-// Radix-2 decimation-in-frequency 8-point DFT, natural-order output.
-__device__ __forceinline__ void dft8(float2 (&a)[8]) {
+// Radix-2 decimation-in-frequency 8-point DFT, natural-order output (28 packed instructions).
+__device__ __forceinline__ void dft8(c64 (&a)[8]) {
   const float r = 0.70710678118654752440f;
-  const float2 b0 = cadd(a[0], a[4]), b1 = cadd(a[1], a[5]), b2 = cadd(a[2], a[6]), b3 = cadd(a[3], a[7]);
-  const float2 b4 = csub(a[0], a[4]);
-  float2 b5 = csub(a[1], a[5]), b6 = csub(a[2], a[6]), b7 = csub(a[3], a[7]);
-  b5 = make_float2(r * (b5.x + b5.y), r * (b5.y - b5.x));   // * W8^1
-  b6 = mul_neg_i(b6);                                       // * W8^2
-  b7 = make_float2(r * (b7.y - b7.x), -r * (b7.x + b7.y));  // * W8^3
-  dft4(b0, b1, b2, b3, a[0], a[2], a[4], a[6]);
-  dft4(b4, b5, b6, b7, a[1], a[3], a[5], a[7]);
+  const c64 b0 = add2(a[0], a[4]), b1 = add2(a[1], a[5]), b2 = add2(a[2], a[6]), b3 = add2(a[3], a[7]);
+  const c64 b4 = sub2(a[0], a[4]), b6 = sub2(a[2], a[6]);
+  c64 b5 = sub2(a[1], a[5]), b7 = sub2(a[3], a[7]);
+  b5 = cmul2(b5, r, -r);     // * W8^1
+  b7 = cmul2(b7, -r, -r);    // * W8^3      (b6 * W8^2 = -i b6 is folded into dft4)
+  dft4<false>(b0, b1, b2, b3, a[0], a[2], a[4], a[6]);
+  dft4<true>(b4, b5, b6, b7, a[1], a[3], a[5], a[7]);
 }
 
 __device__ __forceinline__ void group_sync(int g) {
   asm volatile("bar.sync %0, 64;" ::"r"(g + 1) : "memory");
 }
 
-// BPT = bins per thread, FPB = filters per bin block.  <6, 5> covers the e2e-tts basis (372 bins, 80 Slaney filters),
-// <8, 8> any triangular bank on <= 512 bins the constructor accepts.  The magnitudes are stored with a row pitch of
-// BPT | 1 words per block, so the 64 threads read their blocks with an odd stride (no bank conflicts).
-template <int BPT, int FPB>
+// k1 handled by the thread with (thread >> 3) == h: partners k1 <-> 8 - k1 share a warp (h < 4: {0, 1, 4, 7}; h >= 4:
+// {2, 3, 6, 5}), and the two rows a half-warp reads in pass 2 differ by an odd number of rows (bank-conflict-free with
+// the 72-element row pitch).
+__device__ __forceinline__ int k1_of(int h) { return (0x56327410 >> (4 * h)) & 7; }   // {0,1,4,7,2,3,6,5}
+__device__ __forceinline__ int h_of(int k1) { return (0x36725410 >> (4 * k1)) & 7; }  // inverse: k1 0..7 -> h
+
 __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* audio = reinterpret_cast<float*>(smem);                    // [kAudio]
-  float2* tw_s = reinterpret_cast<float2*>(audio + kAudio);         // [512]
-  float2* sx = tw_s + 512;                                          // [kGroups][2][kSx]
-  float* mag_all = reinterpret_cast<float*>(sx + kGroups * 2 * kSx);  // [kGroups][kMagPad]
-  float* out_s = mag_all + kGroups * kMagPad;                       // [n_mels][kF+1]
-  float* energy_s = out_s + ((p.n_mels * (kF + 1) + 3) & ~3);       // [kF]
+  float2* sx = reinterpret_cast<float2*>(audio + kAudio);           // [kGroups][kSx]
+  float* mag_all = reinterpret_cast<float*>(sx + kGroups * kSx);    // [kF][magp]
+  float* energy_s = mag_all + kF * p.magp;                          // [kF]
   float* red_s = energy_s + kF;                                     // [kGroups][2]
-  constexpr int PITCH = BPT | 1;
-  constexpr int NW4 = (FPB * BPT + 3) / 4;
-  const int part_n = (p.n_mels + 1) * p.fb_split;                   // + the scratch slot row
-  float* part_all = red_s + kGroups * 2;                            // [kGroups][n_mels + 1][fb_split]
-  float4* fb_w_s = reinterpret_cast<float4*>(part_all + ((kGroups * part_n + 3) & ~3));  // [NW4][64]
-  int* fb_slot_s = reinterpret_cast<int*>(fb_w_s + NW4 * 64);       // [FPB][64]
+  float* fbw_s = red_s + kGroups * 2;                               // [n_w]
+  int* meta_s = reinterpret_cast<int*>(fbw_s + ((p.n_w + 3) & ~3)); // [3][n_mels]
 
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * kF;
   const int nf = min(kF, p.T - f0);
 
-  // ---- stage audio (reflect padding resolved here, stft.py:60-64), tables and the sparse filterbank ----
+  // ---- stage audio (reflect padding resolved here, stft.py:60-64) and the sparse filterbank ----
   {
     const float* row = p.wav + (long long)b * p.ldw;
     const long long base = (long long)f0 * kHop - kPad;  // source index of audio[0]
@@ -156,154 +192,143 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
       }
     }
     if (bad && p.range_flag) atomicOr(p.range_flag, 1);
-    for (int i = tid; i < 512; i += kThreads) tw_s[i] = p.tw[i];
-    for (int i = tid; i < NW4 * 64; i += kThreads) fb_w_s[i] = p.fb_w[i];
-    for (int i = tid; i < FPB * 64; i += kThreads) fb_slot_s[i] = p.fb_slot[i];
-    for (int i = tid; i < kGroups * part_n; i += kThreads) part_all[i] = 0.f;   // unused slots stay 0
-    for (int i = tid; i < kGroups * kMagPad; i += kThreads) mag_all[i] = 0.f;   // bins past nb: weight 0 x finite
+    for (int i = tid; i < p.n_w; i += kThreads) fbw_s[i] = p.fb_w[i];
+    for (int i = tid; i < 3 * p.n_mels; i += kThreads) meta_s[i] = p.fb_meta[i];
+    if (nf < kF)   // frames past the clip end: the filterbank pass reads their (unwritten) rows with lanes >= nf
+      for (int i = tid; i < (kF - nf) * p.magp; i += kThreads) mag_all[nf * p.magp + i] = 0.f;
   }
 
   const int g = tid >> 6;   // FFT group
   const int t = tid & 63;   // thread within the group
   const int hi = t >> 3, lo = t & 7;
-  float2* S1 = sx + g * 2 * kSx;
-  float2* S2 = S1 + kSx;
-  float* mag = mag_all + g * kMagPad;
-  float* part = part_all + g * part_n;
+  const int k1 = k1_of(hi);   // passes 2 / 3 and the recombination: this thread's k1
+  float2* S1 = sx + g * kSx;
   const int nb = p.nb;
 
-  // per-thread constants: window taps and twiddles of passes 1 and 2
-  float w0[8], w1[8];
+  // per-thread constants: window taps, the twiddles of passes 1 and 2, the recombination twiddle and partner lane
+  c64 wpair[8];
   float2 t1[8], t2[8];
 #pragma unroll
   for (int n1 = 0; n1 < 8; ++n1) {
-    w0[n1] = p.window[128 * n1 + 2 * t];
-    w1[n1] = p.window[128 * n1 + 2 * t + 1];
+    wpair[n1] = pk2(p.window[128 * n1 + 2 * t], p.window[128 * n1 + 2 * t + 1]);
     t1[n1] = p.tw[2 * ((t * n1) & 511)];    // W_512^(n2 k1), n2 = t
     t2[n1] = p.tw[16 * ((lo * n1) & 63)];   // W_64^(b c),   b = lo
   }
+  const bool self = k1 == 0 && lo == 0;      // holds k = 64 d: its partner bins 64 (8 - d) are its own registers
+  const int k1p = (8 - k1) & 7, cp = k1 ? 7 - lo : (8 - lo) & 7;
+  const int lane_p = ((h_of(k1p) & 3) << 3) | cp;   // lane (within this warp) of the thread that holds 512 - k
+  // X[k] = (s + wk * dd / i) / 2 with s = Z[k] + conj Z[512-k], dd = Z[k] - conj Z[512-k], wk = W_1024^k =
+  // W_1024^(k1 + 8 c) * W_16^d:  gbase = -i/2 * W_1024^(k1 + 8 c)
+  const float2 wb = p.tw[k1 + 8 * lo];
+  const c64 gbase = pk2(0.5f * wb.y, -0.5f * wb.x);
+  c64* S1c = reinterpret_cast<c64*>(S1);
   __syncthreads();
 
   for (int fl = g; fl < nf; fl += kGroups) {
-    float2 a[8];
+    c64 a[8];
     // pass 1: thread n2 = t, points z[64 n1 + n2] = (xw[128 n1 + 2 n2], xw[128 n1 + 2 n2 + 1])
-    const float2* src = reinterpret_cast<const float2*>(audio + fl * kHop) + t;
-    float e = 0.f;  // sum of the squared windowed samples of this thread
+    const c64* src = reinterpret_cast<const c64*>(audio + fl * kHop) + t;
+    c64 e2 = pk2(0.f, 0.f);  // (sum of the squared windowed even samples, ... odd samples) of this thread
 #pragma unroll
     for (int n1 = 0; n1 < 8; ++n1) {
-      const float2 v = src[64 * n1];
-      a[n1] = make_float2(v.x * w0[n1], v.y * w1[n1]);
-      e = fmaf(a[n1].x, a[n1].x, e);
-      e = fmaf(a[n1].y, a[n1].y, e);
+      a[n1] = mul2(src[64 * n1], wpair[n1]);
+      e2 = fma2(a[n1], a[n1], e2);
     }
     dft8(a);
-    S1[t] = a[0];
+    S1c[t] = a[0];
 #pragma unroll
-    for (int k1 = 1; k1 < 8; ++k1) S1[k1 * 72 + t] = cmul(a[k1], t1[k1]);
+    for (int q = 1; q < 8; ++q) S1c[q * 72 + t] = cmul2(a[q], t1[q].x, t1[q].y);
     group_sync(g);
-    // pass 2: thread (k1 = hi, b = lo) reads Y[k1][8 a + b]
+    // pass 2: thread (k1, b = lo) reads Y[k1][8 a + b]
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] = S1[hi * 72 + 8 * q + lo];
+    for (int q = 0; q < 8; ++q) a[q] = S1c[k1 * 72 + 8 * q + lo];
     dft8(a);
-    S2[hi * 72 + lo] = a[0];
+    group_sync(g);   // every thread of the group has read its pass-1 values: the buffer takes the pass-2 results
+    S1c[hi * 72 + lo] = a[0];
 #pragma unroll
-    for (int c = 1; c < 8; ++c) S2[hi * 72 + c * 9 + lo] = cmul(a[c], t2[c]);
+    for (int c = 1; c < 8; ++c) S1c[hi * 72 + c * 9 + lo] = cmul2(a[c], t2[c].x, t2[c].y);
     group_sync(g);
-    // pass 3: thread (k1 = hi, c = lo) reads U[k1][c][b]; result Z[k] , k = k1 + 8 c + 64 d, -> S3[k ^ ((k >> 3) & 7)] (aliases S1;
-    // the xor spreads both this scattered store and the recombination's paired loads over the banks)
+    // pass 3: thread (k1, c = lo) reads U[k1][c][b], b = 0..7 (written by the 8 threads that share k1)
 #pragma unroll
-    for (int q = 0; q < 8; ++q) a[q] = S2[hi * 72 + lo * 9 + q];
-    dft8(a);
-#pragma unroll
-    for (int d = 0; d < 8; ++d) {
-      const int k = hi + 8 * lo + 64 * d;
-      S1[k ^ ((k >> 3) & 7)] = a[d];
-    }
-    group_sync(g);
-    // real-FFT recombination: thread t owns the bin pairs (k, 512 - k), k = t + 64 j, j = 0..3; thread 0 also
-    // bin 256.  Ze = (Z[k] + conj Z[512-k]) / 2, Zo = (Z[k] - conj Z[512-k]) / (2i), X[k] = Ze + W^k Zo,
-    // X[512-k] = conj(Ze - W^k Zo).  k = 0 gives the purely real X[0] and X[512].
+    for (int q = 0; q < 8; ++q) a[q] = S1c[hi * 72 + lo * 9 + q];
+    dft8(a);          // a[d] = Z[k1 + 8 c + 64 d]
+    // real-FFT recombination.  The partner thread sends its register dd, which is Z[512 - k] for this thread's
+    // d = 7 - dd; the thread that holds k = 64 d pairs its own registers d and 8 - d instead.
     float x0sq = 0.f, xnsq = 0.f;
+    float* mrow = mag_all + fl * p.magp;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = t + 64 * j;
-      const int kk = (512 - k) & 511;
-      const float2 za = S1[k ^ ((k >> 3) & 7)];
-      const float2 zb = S1[kk ^ ((kk >> 3) & 7)];
-      const float2 ze = make_float2(0.5f * (za.x + zb.x), 0.5f * (za.y - zb.y));
-      const float2 zo = make_float2(0.5f * (za.y + zb.y), -0.5f * (za.x - zb.x));
-      const float2 wz = cmul(tw_s[k], zo);
-      const float2 x = cadd(ze, wz), xp = csub(ze, wz);
-      const float s = x.x * x.x + x.y * x.y + 1e-9f;  // stft.py:77
-      const float sp = xp.x * xp.x + xp.y * xp.y + 1e-9f;
-      if (k < nb) mag[k + (k / BPT) * (PITCH - BPT)] = sqrt_approx(s);
-      if (512 - k < nb) mag[(512 - k) + ((512 - k) / BPT) * (PITCH - BPT)] = sqrt_approx(sp);
-      if (k == 0) {
-        x0sq = x.x * x.x;
-        xnsq = xp.x * xp.x;
+    for (int dd = 0; dd < 8; ++dd) {
+      float ax, ay;
+      up2(a[dd], ax, ay);
+      float bx = __shfl_sync(0xffffffffu, ax, lane_p);
+      float by = __shfl_sync(0xffffffffu, ay, lane_p);
+      const int d = 7 - dd;
+      if (self) up2(a[(8 - d) & 7], bx, by);
+      const c64 zb = pk2(bx, by);
+      const c64 sm = fma2(zb, pk2(1.f, -1.f), a[d]);    // Z[k] + conj Z[512-k]
+      const c64 df = fma2(zb, pk2(-1.f, 1.f), a[d]);    // Z[k] - conj Z[512-k]
+      // g = gbase * W_16^d
+      constexpr float kC[8] = {1.f, 0.92387953251128675613f, 0.70710678118654752440f, 0.38268343236508977173f,
+                               0.f, -0.38268343236508977173f, -0.70710678118654752440f, -0.92387953251128675613f};
+      constexpr float kS[8] = {0.f, -0.38268343236508977173f, -0.70710678118654752440f, -0.92387953251128675613f,
+                               -1.f, -0.92387953251128675613f, -0.70710678118654752440f, -0.38268343236508977173f};
+      const c64 gd = cmul2(gbase, kC[d], kS[d]);
+      float gx, gy;
+      up2(gd, gx, gy);
+      const c64 wz = cmul2(df, gx, gy);                  // wk * Zo
+      const c64 x = fma2(pk2(0.5f, 0.5f), sm, wz);       // X[k]
+      float xr, xi;
+      up2(x, xr, xi);
+      const int k = k1 + 8 * lo + 64 * d;
+      if (k < nb) mrow[k] = sqrt_approx(fmaf(xr, xr, fmaf(xi, xi, 1e-9f)));   // stft.py:77
+      if (d == 0 && self) {
+        const c64 xp = fma2(pk2(0.5f, 0.5f), sm, mul2(wz, pk2(-1.f, -1.f)));   // X[512] = Ze - W^0 Zo (real)
+        float pr, pi_;
+        up2(xp, pr, pi_);
+        x0sq = xr * xr;
+        xnsq = pr * pr;
+        if (512 < nb) mrow[512] = sqrt_approx(xnsq + 1e-9f);
       }
     }
-    if (t == 0 && 256 < nb) {
-      const float2 z = S1[256];  // 256 ^ ((256 >> 3) & 7)
-      mag[256 + (256 / BPT) * (PITCH - BPT)] = sqrt_approx(z.x * z.x + z.y * z.y + 1e-9f);
-    }
     // energy^2 = sum_{k=0..512} (|X_k|^2 + 1e-9) = (1024 sum xw^2 + X_0^2 + X_512^2) / 2 + 513e-9   (stft.py:84)
-    e = fmaf(1024.f, e, x0sq + xnsq);
+    float e, eo;
+    up2(e2, e, eo);
+    e = fmaf(1024.f, e + eo, x0sq + xnsq);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if ((t & 31) == 0) red_s[g * 2 + (t >> 5)] = e;
-    group_sync(g);
-    // sparse mel filterbank (stft.py:80): thread t applies the FPB x BPT weight block of its bins and leaves one
-    // partial sum per filter in that filter's slot of this thread
-    {
-      float mv[BPT];
-#pragma unroll
-      for (int i = 0; i < BPT; ++i) mv[i] = mag[t * PITCH + i];
-      float w[NW4 * 4];
-#pragma unroll
-      for (int q = 0; q < NW4; ++q) {
-        const float4 v = fb_w_s[q * 64 + t];
-        w[4 * q] = v.x;
-        w[4 * q + 1] = v.y;
-        w[4 * q + 2] = v.z;
-        w[4 * q + 3] = v.w;
-      }
-#pragma unroll
-      for (int j = 0; j < FPB; ++j) {
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < BPT; ++i) acc = fmaf(w[j * BPT + i], mv[i], acc);
-        part[fb_slot_s[j * 64 + t]] = acc;
-      }
-    }
+    group_sync(g);   // (also: every thread has read its pass-2 values before the next frame's pass 1 overwrites them)
     if (t == 0) energy_s[fl] = sqrtf(0.5f * (red_s[g * 2] + red_s[g * 2 + 1]) + 513e-9f);
-    group_sync(g);
-    // fixed-order sum of the partials + log compression (stft.py:81, utils.py:28)
-    for (int m = t; m < p.n_mels; m += 64) {
-      float acc = 0.f;
-      for (int q = 0; q < p.fb_split; ++q) acc += part[m * p.fb_split + q];
-      out_s[m * (kF + 1) + fl] = logf(fmaxf(acc, 1e-5f));
-    }
   }
   __syncthreads();
 
-  // ---- coalesced stores: mel[b][m][f0 .. f0+nf) ----
-  for (int i = tid; i < p.n_mels * kF; i += kThreads) {
-    const int m = i / kF, f = i - m * kF;
-    if (f < nf) p.mel[((long long)b * p.n_mels + m) * p.T + f0 + f] = out_s[m * (kF + 1) + f];
+  // ---- sparse mel filterbank (stft.py:80) + log compression (stft.py:81, utils.py:28), frames on the lanes ----
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const float* mf = mag_all + lane * p.magp;
+    const int* m_lo = meta_s;
+    const int* m_n = meta_s + p.n_mels;
+    const int* m_off = meta_s + 2 * p.n_mels;
+    for (int m = warp; m < p.n_mels; m += kThreads / 32) {
+      const int lo_k = m_lo[m], n = m_n[m];
+      const float* w = fbw_s + m_off[m];
+      float acc = 0.f;
+      for (int i = 0; i < n; ++i) acc = fmaf(w[i], mf[lo_k + i], acc);
+      if (lane < nf) p.mel[((long long)b * p.n_mels + m) * p.T + f0 + lane] = logf(fmaxf(acc, 1e-5f));
+    }
+    if (p.energy && tid < nf) p.energy[(long long)b * p.T + f0 + tid] = energy_s[tid];
   }
-  if (p.energy && tid < nf) p.energy[(long long)b * p.T + f0 + tid] = energy_s[tid];
 }
 
 }  // namespace
 
 struct e2e_mel {
-  int n_fft, hop, win, n_mels, nnz;
-  int nb = 0, split = 1, variant = 0;  // variant 0: mel_kernel<6, 5>, 1: mel_kernel<8, 8>
+  int n_fft, hop, win, n_mels;
+  int nb = 0, magp = 0, n_w = 0;
   float* d_window = nullptr;
   float2* d_tw = nullptr;
-  float4* d_fbw = nullptr;
-  int* d_slot = nullptr;
+  float* d_fbw = nullptr;
+  int* d_meta = nullptr;
   int smem_bytes = 0;
 };
 
@@ -312,70 +337,33 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
   if (!mel_basis || !out) return fail(-1, "null argument");
   if (n_fft != kNfft || win_length != kNfft || hop_length != kHop)
     return fail(-4, "mel front-end supports n_fft == win_length == 1024 and hop_length == 256 (the e2e-tts config)");
-  if (n_mels < 1 || n_mels > 128) return fail(-4, "n_mels must be in [1, 128]");
-  // sparse filterbank in block form: thread t of a frame owns bins [t*BPT, (t+1)*BPT) and the filters overlapping them
-  int nb = 1, nnz = 0;
-  for (int r = 0; r < n_mels; ++r)
+  if (n_mels < 1 || n_mels > kMaxMels) return fail(-4, "n_mels must be in [1, 128]");
+  // sparse filterbank: per filter the span [lo, hi] of its non-zero bins (zeros inside the span are kept as weights)
+  std::vector<int> meta(3 * (size_t)n_mels, 0);
+  std::vector<float> wpk;
+  int nb = 1;
+  for (int r = 0; r < n_mels; ++r) {
+    int lo = -1, hi = -1;
     for (int k = 0; k < kBins; ++k)
       if (mel_basis[(size_t)r * kBins + k] != 0.f) {
-        ++nnz;
-        nb = k + 1 > nb ? k + 1 : nb;
+        if (lo < 0) lo = k;
+        hi = k;
       }
-  if (nb > 512) return fail(-4, "mel filterbank reaches the Nyquist bin: unsupported (fmax must be below sr/2)");
-  int variant = -1, BPT = 0, FPB = 0, split = 1;
-  std::vector<float> wblk;
-  std::vector<int> slot;
-  for (int v = 0; v < 2 && variant < 0; ++v) {
-    BPT = v == 0 ? 6 : 8;
-    FPB = v == 0 ? 5 : 8;
-    if (64 * BPT < nb) continue;
-    const int nw4 = (FPB * BPT + 3) / 4;
-    // filters of every block, and the blocks of every filter
-    std::vector<std::vector<int>> filt(64);
-    std::vector<int> first(n_mels, -1), count(n_mels, 0);
-    bool fits = true;
-    for (int t = 0; t < 64 && fits; ++t)
-      for (int r = 0; r < n_mels; ++r) {
-        bool any = false;
-        for (int i = 0; i < BPT; ++i) {
-          const int k = t * BPT + i;
-          any = any || (k < kBins && mel_basis[(size_t)r * kBins + k] != 0.f);
-        }
-        if (!any) continue;
-        filt[t].push_back(r);
-        if (first[r] < 0) first[r] = t;
-        count[r] = t - first[r] + 1;  // blocks first..t (a gap inside a filter just leaves a zero partial)
-        if ((int)filt[t].size() > FPB) fits = false;
-      }
-    if (!fits) continue;
-    split = 1;
-    for (int r = 0; r < n_mels; ++r) split = count[r] > split ? count[r] : split;
-    if (split > kFbSplitMax) continue;
-    variant = v;
-    wblk.assign((size_t)nw4 * 4 * 64, 0.f);
-    slot.assign((size_t)FPB * 64, n_mels * split);  // unused filters of a block -> the scratch slot row
-    for (int t = 0; t < 64; ++t)
-      for (size_t j = 0; j < filt[t].size(); ++j) {
-        const int r = filt[t][j];
-        slot[j * 64 + t] = r * split + (t - first[r]);
-        for (int i = 0; i < BPT; ++i) {
-          const int k = t * BPT + i;
-          const int e = (int)j * BPT + i;  // element e of the thread's block lives in float4 e/4, lane e%4
-          wblk[((size_t)(e / 4) * 64 + t) * 4 + (e % 4)] = k < kBins ? mel_basis[(size_t)r * kBins + k] : 0.f;
-        }
-      }
+    meta[r] = lo < 0 ? 0 : lo;
+    meta[n_mels + r] = lo < 0 ? 0 : hi - lo + 1;
+    meta[2 * n_mels + r] = (int)wpk.size();
+    for (int k = lo; lo >= 0 && k <= hi; ++k) wpk.push_back(mel_basis[(size_t)r * kBins + k]);
+    if (hi + 1 > nb) nb = hi + 1;
   }
-  if (variant < 0)
-    return fail(-4, "mel filterbank does not fit the kernel's block form (<= 8 filters per 8-bin block, <= 12 blocks per filter)");
+  if (wpk.empty()) wpk.push_back(0.f);
   e2e_mel* m = new e2e_mel;
   m->n_fft = n_fft;
   m->hop = hop_length;
   m->win = win_length;
   m->n_mels = n_mels;
-  m->nnz = nnz;
   m->nb = nb;
-  m->split = split;
-  m->variant = variant;
+  m->magp = nb | 1;
+  m->n_w = (int)wpk.size();
   std::vector<float> window(kNfft);
   std::vector<float2> tw(kNfft);
   const double pi = 3.14159265358979323846;
@@ -384,13 +372,8 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
     tw[n] = make_float2((float)cos(2.0 * pi * n / kNfft), (float)(-sin(2.0 * pi * n / kNfft)));
   }
   // mirrors the carve-up at the top of mel_kernel
-  {
-    const int part_n = (n_mels + 1) * split;
-    const int nw4 = (FPB * BPT + 3) / 4;
-    m->smem_bytes = (kAudio + 2 * 512 + kGroups * 2 * kSx * 2 + kGroups * kMagPad + ((n_mels * (kF + 1) + 3) & ~3) + kF +
-                     kGroups * 2 + ((kGroups * part_n + 3) & ~3) + nw4 * 4 * 64 + FPB * 64) * 4;
-  }
-  if (m->smem_bytes > 113 * 1024) {
+  m->smem_bytes = (kAudio + 2 * kGroups * kSx + kF * m->magp + kF + kGroups * 2 + ((m->n_w + 3) & ~3) + 3 * n_mels) * 4;
+  if (m->smem_bytes > 227 * 1024) {
     delete m;
     return fail(-4, "mel filterbank too dense for the shared-memory budget");
   }
@@ -402,11 +385,10 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
   };
   up((void**)&m->d_window, window.data(), window.size() * 4);
   up((void**)&m->d_tw, tw.data(), tw.size() * 8);
-  up((void**)&m->d_fbw, wblk.data(), wblk.size() * 4);
-  up((void**)&m->d_slot, slot.data(), slot.size() * 4);
+  up((void**)&m->d_fbw, wpk.data(), wpk.size() * 4);
+  up((void**)&m->d_meta, meta.data(), meta.size() * 4);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(variant == 0 ? mel_kernel<6, 5> : mel_kernel<8, 8>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
+    e = cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
   if (e != cudaSuccess) {
     e2e_mel_destroy(m);
     return fail((int)e, std::string("e2e_mel_create: ") + cudaGetErrorString(e));
@@ -420,7 +402,7 @@ extern "C" void e2e_mel_destroy(e2e_mel* m) {
   cudaFree(m->d_window);
   cudaFree(m->d_tw);
   cudaFree(m->d_fbw);
-  cudaFree(m->d_slot);
+  cudaFree(m->d_meta);
   delete m;
 }
 
@@ -445,21 +427,18 @@ extern "C" int e2e_mel_forward(e2e_mel* m, const float* wav, int32_t B, int64_t 
   p.B = B;
   p.T = (int)T;
   p.n_mels = m->n_mels;
-  p.nnz = m->nnz;
   p.nb = m->nb;
-  p.fb_split = m->split;
+  p.magp = m->magp;
+  p.n_w = m->n_w;
   p.mel = mel;
   p.energy = energy;
   p.range_flag = range_flag;
   p.window = m->d_window;
   p.tw = m->d_tw;
   p.fb_w = m->d_fbw;
-  p.fb_slot = m->d_slot;
+  p.fb_meta = m->d_meta;
   dim3 grid((unsigned)((T + kF - 1) / kF), (unsigned)B);
-  if (m->variant == 0)
-    mel_kernel<6, 5><<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
-  else
-    mel_kernel<8, 8><<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  mel_kernel<<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("mel_kernel launch: ") + cudaGetErrorString(e));
   return 0;

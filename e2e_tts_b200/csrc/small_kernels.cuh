@@ -17,7 +17,8 @@
 namespace e2e {
 
 __global__ void mel_to_act_kernel(const float* __restrict__ mel, long long sB, long long sC, long long sT, int B,
-                                  int T, int C, int cpad, __nv_bfloat16* __restrict__ out, int f16) {
+                                  int T, int C, int cpad, __nv_bfloat16* __restrict__ out, int f16,
+                                  float slope = 1.0f) {   // slope < 1: store leaky_relu(x, slope) (standalone resblocks)
   const int G = cpad / 8;
   const long long total = (long long)B * T * G;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -29,8 +30,10 @@ __global__ void mel_to_act_kernel(const float* __restrict__ mel, long long sB, l
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int c0 = g * 8 + 2 * i;
-    const float a = c0 < C ? mel[b * sB + c0 * sC + t * sT] : 0.f;
-    const float c = c0 + 1 < C ? mel[b * sB + (c0 + 1) * sC + t * sT] : 0.f;
+    float a = c0 < C ? mel[b * sB + c0 * sC + t * sT] : 0.f;
+    float c = c0 + 1 < C ? mel[b * sB + (c0 + 1) * sC + t * sT] : 0.f;
+    a = fmaxf(a, a * slope);
+    c = fmaxf(c, c * slope);
     pk[i] = pack16(a, c, f16);
   }
   *reinterpret_cast<uint4*>(out + ((long long)b * T + t) * cpad + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -182,6 +185,24 @@ postnet_out_kernel(const float* __restrict__ y, const float* __restrict__ x, lon
   float v = y[row * ldy + c];
   if (x) v += x[idx];
   out[idx] = v;
+}
+
+// ---- standalone resblocks: y [B][T][C] fp32 (channels-last GEMM output) -> out [B][C][T] fp32 (the modules' layout),
+// 32 x 32 tiles through shared memory so that both sides are coalesced ----
+__global__ void __launch_bounds__(256)
+cl_to_ncl_kernel(const float* __restrict__ y, float* __restrict__ out, int T, int C) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, c = c0 + tx;
+    tile[r][tx] = (t < T && c < C) ? y[((long long)b * T + t) * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, t = t0 + tx;
+    if (c < C && t < T) out[((long long)b * C + c) * T + t] = tile[tx][r];
+  }
 }
 
 // ---- iSTFTNet head (class iSTFT, generator.py:91-109) ----

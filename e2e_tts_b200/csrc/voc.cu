@@ -2,6 +2,7 @@
 // Mirrors the structure of the reference generator (e2e_tts/models/vocoder/generator.py:13-53 and
 // layers.py:10-69) as a list of tcgen05 convolution launches plus two small CUDA-core kernels.
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <string>
@@ -22,7 +23,11 @@ struct Layer {
   LayerKind kind;
   int cin, cout, k, dil, u;  // reference shapes (u = stride of ConvTranspose1d)
   ConvShape shape;           // GEMM form (L_CONV / L_CONVT)
-  uint8_t* d_w = nullptr;    // packed bf16 weights (or fp32 [k][cin] for L_POST)
+  // Narrower N tilings of the same GEMM (nt = 128, 64) with their own packed images: small batches leave most SMs
+  // without a unit when a 256-column layer is one N tile per 128 rows, so make_conv_op may split N across CTAs
+  std::vector<ConvShape> alt_shape;
+  std::vector<uint8_t*> alt_w;
+  uint8_t* d_w = nullptr;    // packed 16-bit weights (or fp32 [k][cin] for L_POST)
   float* d_bias = nullptr;   // [n_total]
   std::vector<float> h_bias;  // host copy (the fused pair kernel takes its biases as kernel parameters)
   float post_bias = 0.f;
@@ -47,6 +52,25 @@ struct PlanKey {
   }
 };
 
+// CUDA-graph replay of a whole forward: the launch sequence of one (plan, input, output) combination is captured the
+// second time it is seen and replayed from then on (serving loops reuse their device buffers: e2e_tts_b200.HostPipeline,
+// `out=`), which takes the ~50 kernel launches of a forward off the host's critical path - what bounds single-utterance
+// latency when the kernels are short (e2e_tts/src/api/utils.py:131-145 synthesises one bucket at a time).
+struct GraphKey {
+  int B, T;
+  const void *ws, *mel, *o1, *o2, *o3;
+  long long sB, sC, sT;
+  float scale;
+  bool operator<(const GraphKey& o) const {
+    return std::memcmp(this, &o, sizeof(GraphKey)) < 0;
+  }
+};
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  int seen = 0;
+  bool failed = false;
+};
+
 // Activations live in HBM ONCE, as bf16 leaky_relu(x): that tensor is both the next convolution's operand and
 // (through the inverse LeakyReLU) the residual x of `xt + x`.  The running resblock sum `xs` (generator.py:44-47)
 // ping-pongs between two bf16 buffers.
@@ -64,14 +88,25 @@ struct e2e_voc {
   std::vector<Layer> layers;
   std::map<std::string, int> by_name;
   std::map<PlanKey, std::vector<Op>> plans;
+  std::map<GraphKey, GraphEntry> graphs;
   int cin_pad = 0;
   int hop = 1;
   int n_sms = 148;
   int f16 = 0;   // operand / activation format of the tensor-core path: 0 = bf16, 1 = fp16 (e2e_voc_set_operand_dtype)
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;  // one-shot profiling events
   int last_launches = 0;
+  int last_graph = 0;   // 1: the last forward was replayed from a captured CUDA graph
+  cudaStream_t cap_stream = nullptr;   // capture-only stream (never executes anything)
   PostWeights<7 * 32> post_w{};                      // conv_post weights [k][C] for the 32-channel, k = 7 kernel
 };
+
+// Launch plans (and the graphs captured from them) embed biases and weight pointers: forget them when weights change.
+static void drop_plans(e2e_voc* v) {
+  v->plans.clear();
+  for (auto& kv : v->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  v->graphs.clear();
+}
 
 static int pick_nt(int cout) { return cout >= 256 ? 256 : cout; }
 
@@ -93,6 +128,17 @@ static void add_conv(e2e_voc* v, const std::string& name, int cin, int cin_pad, 
   const int n_tiles = cout_pad / L.shape.nt;
   for (int i = 0; i < n_tiles; ++i)
     for (int j = 0; j < k; ++j) L.shape.shifts.push_back((j - (k - 1) / 2) * dil);
+  if (L.shape.nt == 256)
+    for (int nt : {128, 64}) {
+      if (cout_pad / nt > kMaxNTiles) continue;
+      ConvShape a = L.shape;
+      a.nt = nt;
+      a.shifts.clear();
+      for (int i = 0; i < cout_pad / nt; ++i)
+        for (int j = 0; j < k; ++j) a.shifts.push_back((j - (k - 1) / 2) * dil);
+      L.alt_shape.push_back(a);
+      L.alt_w.push_back(nullptr);
+    }
   v->by_name[name] = (int)v->layers.size();
   v->layers.push_back(L);
 }
@@ -212,7 +258,12 @@ extern "C" void e2e_voc_destroy(e2e_voc* v) {
   for (auto& L : v->layers) {
     if (L.d_w) cudaFree(L.d_w);
     if (L.d_bias) cudaFree(L.d_bias);
+    for (uint8_t* w : L.alt_w)
+      if (w) cudaFree(w);
   }
+  for (auto& kv : v->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (v->cap_stream) cudaStreamDestroy(v->cap_stream);
   delete v;
 }
 
@@ -231,11 +282,13 @@ extern "C" int e2e_voc_set_operand_dtype(e2e_voc* v, int32_t dtype) {
   if (v->f16 == dtype) return 0;
   v->f16 = dtype;
   for (auto& L : v->layers) L.loaded = false;   // the packed weight images depend on the format: reload every layer
-  v->plans.clear();
+  drop_plans(v);
   return 0;
 }
 
 extern "C" int e2e_voc_operand_dtype(const e2e_voc* v) { return v ? v->f16 : -1; }
+
+extern "C" int e2e_voc_last_forward_was_graph(const e2e_voc* v) { return v ? v->last_graph : -1; }
 
 extern "C" int e2e_voc_missing_layers(const e2e_voc* v) {
   if (!v) return -1;
@@ -268,7 +321,7 @@ extern "C" int e2e_voc_load_layer(e2e_voc* v, const char* name, const float* wei
     L.post_bias = bias[0];
     if (w.size() == sizeof(v->post_w.w) / sizeof(float)) memcpy(v->post_w.w, w.data(), sizeof(v->post_w.w));
     L.loaded = true;
-    v->plans.clear();
+    drop_plans(v);
     return 0;
   }
   const ConvShape& s = L.shape;
@@ -307,9 +360,16 @@ extern "C" int e2e_voc_load_layer(e2e_voc* v, const char* name, const float* wei
     return fail((int)e, "cudaMemcpy");
   if ((e = cudaMemcpy(L.d_bias, bg.data(), bg.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess)
     return fail((int)e, "cudaMemcpy");
+  for (size_t a = 0; a < L.alt_shape.size(); ++a) {
+    std::vector<uint8_t> pk(packed_weight_bytes(L.alt_shape[a]));
+    pack_conv_weights(L.alt_shape[a], wg.data(), pk.data(), v->f16);
+    if (!L.alt_w[a] && (e = cudaMalloc(&L.alt_w[a], pk.size())) != cudaSuccess) return fail((int)e, "cudaMalloc");
+    if ((e = cudaMemcpy(L.alt_w[a], pk.data(), pk.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return fail((int)e, "cudaMemcpy");
+  }
   L.h_bias = bg;
   L.loaded = true;
-  v->plans.clear();
+  drop_plans(v);
   return 0;
 }
 
@@ -365,7 +425,28 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
   Op op;
   op.kind = 1;
   op.layer = layer;
-  const ConvShape& s = L.shape;
+  // N tiling: the layer's natural one, or - when that leaves most SMs idle - a narrower one (more units, cheaper MMAs).
+  // Cost model per 128 rows: rounds of the persistent grid x cycles per MMA (N <= 64: 54, shared-memory A-operand bound;
+  // N = 128: 64; N = 256: 128; profiles/r01_umma_rate_microbench.log) x N tiles a CTA walks per unit.
+  int pick = -1;
+  {
+    static const char* esp = std::getenv("E2E_NO_NSPLIT");
+    auto cost = [&](const ConvShape& cs) {
+      const long long units = (long long)((T + 127) / 128) * (cs.n_total / cs.nt) * B;
+      const long long rounds = (units + v->n_sms - 1) / v->n_sms;
+      return (double)rounds * (cs.nt >= 256 ? 128.0 : (cs.nt >= 128 ? 64.0 : 54.0));
+    };
+    double best = cost(L.shape);
+    for (size_t a = 0; a < L.alt_shape.size() && !esp; ++a) {
+      const double c = cost(L.alt_shape[a]);
+      if (L.alt_w[a] && c < best * 0.9) {
+        best = c;
+        pick = (int)a;
+      }
+    }
+  }
+  const ConvShape& s = pick >= 0 ? L.alt_shape[pick] : L.shape;
+  uint8_t* const w_img = pick >= 0 ? L.alt_w[pick] : L.d_w;
   // Units per CTA of the persistent grid are quantised: pick the tile height (128*mt rows) with the best
   // balance, preferring taller tiles (fewer weight re-streams per row) when the balance is within 6 %.
   const int n_tiles = s.n_total / s.nt;
@@ -396,8 +477,8 @@ static int make_conv_op(e2e_voc* v, std::vector<Op>& ops, int layer, int B, int 
   if (rc) return rc;
   rc = make_act_tensor_map(&op.plan.tm, in, B, T, s.cin, p.rowb / 2, p.box_rows);
   if (rc) return rc;
-  p.w = L.d_w;
-  rc = conv_weight_map(op.plan, L.d_w);
+  p.w = w_img;
+  rc = conv_weight_map(op.plan, w_img);
   if (rc) return rc;
   conv_set_bias(op.plan, L.d_bias, L.h_bias.data(), (int)L.h_bias.size(), L.kind == L_CONVT ? L.cout : 0);
   p.res_act = res_act;
@@ -668,7 +749,7 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
     std::vector<Op> ops;
     int rc = build_plan(v, B, T, workspace, ops);
     if (rc) return rc;
-    if (v->plans.size() > 64) v->plans.clear();
+    if (v->plans.size() > 64) drop_plans(v);
     it = v->plans.emplace(key, std::move(ops)).first;
   }
   Buffers bf;
@@ -680,6 +761,57 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
       first_conv = i < first_conv ? i : first_conv;
       last_conv = i;
     }
+  // ---- CUDA-graph replay (see GraphKey): second sighting of the same buffers captures, later ones replay ----
+  static const bool graphs_on = std::getenv("E2E_NO_GRAPH") == nullptr;
+  GraphEntry* ge = nullptr;
+  bool capturing = false;
+  if (graphs_on && !v->ev_begin && !v->ev_end) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone) {
+      GraphKey gk;
+      std::memset(&gk, 0, sizeof gk);
+      gk.B = B;
+      gk.T = T;
+      gk.ws = workspace;
+      gk.mel = mel;
+      gk.o1 = post.wav ? (const void*)post.wav : (const void*)post.pcm;
+      gk.o2 = so.spec ? (const void*)so.spec : (const void*)post.lens;
+      gk.o3 = so.phase;
+      gk.sB = sB;
+      gk.sC = sC;
+      gk.sT = sT;
+      gk.scale = post.scale;
+      if (v->graphs.size() > 32 && v->graphs.find(gk) == v->graphs.end()) {
+        for (auto& kv : v->graphs)
+          if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        v->graphs.clear();
+      }
+      ge = &v->graphs[gk];
+      ++ge->seen;
+      if (ge->exec) {
+        cudaError_t e = cudaGraphLaunch(ge->exec, st);
+        if (e != cudaSuccess) return fail((int)e, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+        v->last_launches = (int)ops.size();
+        v->last_graph = 1;
+        return 0;
+      }
+      if (ge->seen >= 2 && !ge->failed) {
+        // captured on a stream of the handle's own (the caller's may be the legacy default stream, which cannot be
+        // captured); nothing executes during capture, the instantiated graph is then launched on the caller's stream
+        if (!v->cap_stream && cudaStreamCreateWithFlags(&v->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
+          v->cap_stream = nullptr;
+        if (v->cap_stream && cudaStreamBeginCapture(v->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+          capturing = true;
+        } else {
+          cudaGetLastError();
+          ge->failed = true;
+        }
+      }
+    }
+  }
+  v->last_graph = 0;
+  const cudaStream_t user_st = st;
+  if (capturing) st = v->cap_stream;
   for (size_t oi = 0; oi < ops.size(); ++oi) {
     const Op& op = ops[oi];
     if (oi == first_conv && v->ev_begin) cudaEventRecord(v->ev_begin, st);
@@ -723,6 +855,24 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
   }
   v->ev_begin = v->ev_end = nullptr;
   v->last_launches = (int)ops.size();
+  if (capturing) {
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (e == cudaSuccess && g) {
+      e = cudaGraphInstantiate(&ge->exec, g, 0);
+      cudaGraphDestroy(g);
+    }
+    if (e != cudaSuccess || !ge->exec) {   // capture is an optimisation: enqueue this call directly and do not try again
+      cudaGetLastError();
+      ge->exec = nullptr;
+      ge->failed = true;
+      int rc = voc_forward_impl(v, mel, sB, sC, sT, B, T, post, so, workspace, workspace_bytes, stream);
+      return rc;
+    }
+    e = cudaGraphLaunch(ge->exec, user_st);
+    if (e != cudaSuccess) return fail((int)e, std::string("cudaGraphLaunch: ") + cudaGetErrorString(e));
+    v->last_graph = 1;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("e2e_voc_forward launch: ") + cudaGetErrorString(e));
   return 0;
@@ -910,6 +1060,157 @@ extern "C" int e2e_postnet_forward(e2e_postnet* pn, const float* x, int32_t B, i
   v->last_launches = (int)it->second.size() + 2;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("e2e_postnet_forward launch: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Standalone residual blocks: ResBlock1.forward / ResBlock2.forward (e2e_tts/models/vocoder/layers.py:33-40,60-65) as
+// callable modules, on the same tcgen05 convolution kernel as the generator (every conv its own conv_tc launch; the
+// fused pair / whole-resblock kernels are the generator's arrangement).  x, out: fp32 [B][C][T] (out contiguous).
+// ---------------------------------------------------------------------------------------------------
+struct e2e_resblock {
+  e2e_voc core;
+  int kind = 1, C = 0, k = 3, nd = 0;
+  int dil[E2E_MAX_DILATIONS] = {0};
+};
+
+extern "C" int e2e_resblock_create(int32_t kind, int32_t channels, int32_t kernel_size, const int32_t* dilations,
+                                   int32_t n_dilations, e2e_resblock** out) {
+  if (!out || !dilations) return fail(-1, "null argument");
+  if (kind != 1 && kind != 2) return fail(-1, "kind must be 1 (ResBlock1) or 2 (ResBlock2)");
+  if (channels != 32 && (channels % 64 != 0 || channels < 64 || channels > 512))
+    return fail(-4, "resblock: channels must be 32 or a multiple of 64, <= 512");
+  if (!(kernel_size & 1) || kernel_size < 1 || kernel_size > kMaxTaps) return fail(-4, "resblock: odd kernel size <= 15");
+  if (n_dilations < 1 || n_dilations > E2E_MAX_DILATIONS) return fail(-1, "bad number of dilations");
+  std::unique_ptr<e2e_resblock> rb(new e2e_resblock);
+  rb->kind = kind;
+  rb->C = channels;
+  rb->k = kernel_size;
+  rb->nd = n_dilations;
+  e2e_voc* v = &rb->core;
+  v->cfg = e2e_voc_config{};
+  v->cfg.in_channels = channels;
+  v->cfg.upsample_initial_channel = channels;
+  v->cin_pad = channels;
+  for (int m = 0; m < n_dilations; ++m) {
+    const int d = dilations[m];
+    if (d < 1 || (kernel_size - 1) / 2 * d > 127) return fail(-4, "resblock: dilated receptive field too wide");
+    rb->dil[m] = d;
+    if (kind == 1) {
+      add_conv(v, "convs1." + std::to_string(m), channels, channels, channels, kernel_size, d);
+      add_conv(v, "convs2." + std::to_string(m), channels, channels, channels, kernel_size, 1);
+    } else {
+      add_conv(v, "convs." + std::to_string(m), channels, channels, channels, kernel_size, d);
+    }
+  }
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return fail((int)e, std::string("cudaGetDevice: ") + cudaGetErrorString(e));
+  cudaDeviceGetAttribute(&v->n_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (v->n_sms < 1) v->n_sms = 148;
+  int rc = conv_kernels_init();
+  if (rc) return rc;
+  *out = rb.release();
+  return 0;
+}
+
+extern "C" void e2e_resblock_destroy(e2e_resblock* rb) {
+  if (!rb) return;
+  for (auto& L : rb->core.layers) {
+    if (L.d_w) cudaFree(L.d_w);
+    if (L.d_bias) cudaFree(L.d_bias);
+    for (uint8_t* w : L.alt_w)
+      if (w) cudaFree(w);
+  }
+  delete rb;
+}
+
+extern "C" int e2e_resblock_load_layer(e2e_resblock* rb, const char* name, const float* weight, int64_t weight_numel,
+                                       const float* bias, int64_t bias_numel) {
+  if (!rb) return fail(-1, "null argument");
+  return e2e_voc_load_layer(&rb->core, name, weight, weight_numel, bias, bias_numel);
+}
+
+static void resblock_carve(const e2e_resblock* rb, int B, int T, void* ws, __nv_bfloat16** xin, __nv_bfloat16** mid,
+                           __nv_bfloat16** p0, __nv_bfloat16** p1, float** y, size_t* total) {
+  uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    uint8_t* r = p ? p + off : nullptr;
+    off += align_up(bytes, 1024);
+    return r;
+  };
+  const size_t n = (size_t)B * T * rb->C;
+  *xin = (__nv_bfloat16*)take(n * 2);
+  *mid = (__nv_bfloat16*)take(n * 2);
+  *p0 = (__nv_bfloat16*)take(n * 2);
+  *p1 = (__nv_bfloat16*)take(n * 2);
+  *y = (float*)take(n * 4);
+  *total = off;
+}
+
+extern "C" size_t e2e_resblock_workspace_bytes(const e2e_resblock* rb, int32_t B, int32_t T) {
+  if (!rb || B < 1 || T < 1) return 0;
+  __nv_bfloat16 *a, *b, *c, *d;
+  float* y;
+  size_t total;
+  resblock_carve(rb, B, T, nullptr, &a, &b, &c, &d, &y, &total);
+  return total;
+}
+
+extern "C" int e2e_resblock_forward(e2e_resblock* rb, const float* x, int64_t sB, int64_t sC, int64_t sT, int32_t B,
+                                    int32_t T, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!rb || !x || !out || !workspace) return fail(-1, "null argument");
+  if (B < 1 || T < 1 || B > 65535) return fail(-1, "B in [1, 65535] and T >= 1 required");
+  e2e_voc* v = &rb->core;
+  if (e2e_voc_missing_layers(v) != 0) return fail(-7, "e2e_resblock_forward before all layers were loaded");
+  if (reinterpret_cast<uintptr_t>(workspace) % 1024) return fail(-1, "workspace must be 1024-byte aligned");
+  if (workspace_bytes < e2e_resblock_workspace_bytes(rb, B, T)) return fail(-1, "workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  __nv_bfloat16 *xin, *mid, *p0, *p1;
+  float* y;
+  size_t total;
+  resblock_carve(rb, B, T, workspace, &xin, &mid, &p0, &p1, &y, &total);
+  PlanKey key{B, T, workspace};
+  auto it = v->plans.find(key);
+  if (it == v->plans.end()) {
+    std::vector<Op> ops;
+    const __nv_bfloat16* ain = xin;   // bf16 leaky_relu(x, 0.1): conv operand and (inverted) residual
+    for (int m = 0; m < rb->nd; ++m) {
+      const bool last = m + 1 == rb->nd;
+      __nv_bfloat16* nxt = (m & 1) ? p1 : p0;
+      int rc;
+      if (rb->kind == 1) {
+        rc = make_conv_op(v, ops, v->by_name["convs1." + std::to_string(m)], B, T, ain, nullptr, nullptr, nullptr, mid,
+                          0.1f, 0.f);
+        if (rc) return rc;
+        rc = make_conv_op(v, ops, v->by_name["convs2." + std::to_string(m)], B, T, mid, ain, nullptr, last ? y : nullptr,
+                          last ? nullptr : nxt, 0.1f, 0.f);
+      } else {
+        rc = make_conv_op(v, ops, v->by_name["convs." + std::to_string(m)], B, T, ain, ain, nullptr, last ? y : nullptr,
+                          last ? nullptr : nxt, 0.1f, 0.f);
+      }
+      if (rc) return rc;
+      ain = nxt;
+    }
+    if (v->plans.size() > 16) drop_plans(v);
+    it = v->plans.emplace(key, std::move(ops)).first;
+  }
+  {
+    const long long tot = (long long)B * T * (rb->C / 8);
+    mel_to_act_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, sB, sC, sT, B, T, rb->C, rb->C, xin, v->f16, 0.1f);
+  }
+  for (const Op& op : it->second) {
+    int rc = launch_conv(op.plan, st);
+    if (rc) return rc;
+  }
+  {
+    dim3 grid((T + 31) / 32, (rb->C + 31) / 32, B);
+    cl_to_ncl_kernel<<<grid, 256, 0, st>>>(y, out, T, rb->C);
+  }
+  v->last_launches = (int)it->second.size() + 2;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail((int)e, std::string("e2e_resblock_forward launch: ") + cudaGetErrorString(e));
   return 0;
 }
 

@@ -92,14 +92,101 @@ class _WNConv(nn.Module):
         self.weight = nn.Parameter(w.to(dev))
 
 
-class ResBlock1(nn.Module):
-    """layers.py:10-46 — 3 x [lrelu -> conv(k, d_i) -> lrelu -> conv(k, 1) -> + x]."""
+class _ResBlockBase(nn.Module):
+    """Shared native plumbing of the standalone ResBlock1 / ResBlock2 modules (inside HifiGan the same convolutions run
+    through the generator's fused launches; these classes are then parameter holders)."""
+
+    _kind = 1
+
+    def _rb_layers(self) -> List[tuple]:
+        raise NotImplementedError
+
+    def _rb_init(self) -> None:
+        self._rb_handle = None
+        self._rb_device = None
+        self._rb_version = None
+        self._rb_ws: Dict[tuple, torch.Tensor] = {}
+
+    def _rb_sync(self, device: torch.device) -> None:
+        L = _native.lib()
+        if self._rb_handle is not None and self._rb_device != device:
+            L.e2e_resblock_destroy(self._rb_handle)
+            self._rb_handle = None
+            self._rb_ws.clear()
+        if self._rb_handle is None:
+            h = ctypes.c_void_p()
+            dil = (ctypes.c_int32 * len(self.dilation))(*[int(d) for d in self.dilation])
+            _native.check(L.e2e_resblock_create(self._kind, int(self.channels), int(self.kernel_size), dil,
+                                                len(self.dilation), ctypes.byref(h)), "e2e_resblock_create")
+            self._rb_handle, self._rb_device, self._rb_version = h, device, None
+        fp = tuple((id(p), p._version) for p in self.parameters())
+        if self._rb_version == fp:
+            return
+        for name, layer in self._rb_layers():
+            w = layer.folded_weight().cpu().contiguous()
+            b = layer.bias.detach().float().cpu().contiguous()
+            _native.check(L.e2e_resblock_load_layer(self._rb_handle, name.encode(),
+                                                    ctypes.cast(w.data_ptr(), ctypes.POINTER(ctypes.c_float)), w.numel(),
+                                                    ctypes.cast(b.data_ptr(), ctypes.POINTER(ctypes.c_float)), b.numel()),
+                          "e2e_resblock_load_layer(%s)" % name)
+        self._rb_version = fp
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: [B, channels, T] float32 CUDA tensor (any strides) -> [B, channels, T] float32.  Inference only."""
+        if not isinstance(x, torch.Tensor) or x.dim() != 3 or x.shape[1] != self.channels:
+            raise ValueError("expected a [B, %d, T] tensor, got %s" % (self.channels, tuple(getattr(x, "shape", ()))))
+        if not x.is_cuda:
+            raise RuntimeError("e2e_tts_b200 residual blocks run on CUDA (sm_100a) only; there is no CPU path")
+        if x.dtype != torch.float32:
+            raise ValueError("expected float32 input, got %s" % x.dtype)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise RuntimeError("e2e_tts_b200 residual blocks are inference-only; call them under torch.no_grad()")
+        B, C, T = x.shape
+        if B == 0 or T == 0:
+            return x.new_zeros((B, C, T))
+        with torch.cuda.device(x.device):
+            self._rb_sync(x.device)
+            L = _native.lib()
+            key = (B, T, str(x.device))
+            ws = self._rb_ws.get(key)
+            if ws is None:
+                nbytes = int(L.e2e_resblock_workspace_bytes(self._rb_handle, B, T))
+                if len(self._rb_ws) >= 4:
+                    self._rb_ws.clear()
+                ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=x.device)
+                self._rb_ws[key] = ws
+            ws_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+            out = torch.empty((B, C, T), dtype=torch.float32, device=x.device)
+            rc = L.e2e_resblock_forward(self._rb_handle, x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), B, T,
+                                        out.data_ptr(), ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()),
+                                        torch.cuda.current_stream(x.device).cuda_stream)
+            _native.check(rc, "e2e_resblock_forward")
+        return out
+
+    def __del__(self):
+        try:
+            if getattr(self, "_rb_handle", None) is not None:
+                _native.lib().e2e_resblock_destroy(self._rb_handle)
+                self._rb_handle = None
+        except Exception:
+            pass
+
+
+class ResBlock1(_ResBlockBase):
+    """layers.py:10-46 - 3 x [lrelu -> conv(k, d_i) -> lrelu -> conv(k, 1) -> + x]."""
+
+    _kind = 1
 
     def __init__(self, channels: int, kernel_size: int = 3, dilation=(1, 3, 5)) -> None:
         super().__init__()
         self.channels, self.kernel_size, self.dilation = channels, kernel_size, tuple(dilation)
         self.convs1 = nn.ModuleList([_WNConv(channels, channels, kernel_size) for _ in self.dilation])
         self.convs2 = nn.ModuleList([_WNConv(channels, channels, kernel_size) for _ in self.dilation])
+        self._rb_init()
+
+    def _rb_layers(self) -> List[tuple]:
+        return ([("convs1.%d" % m, l) for m, l in enumerate(self.convs1)] +
+                [("convs2.%d" % m, l) for m, l in enumerate(self.convs2)])
 
     def remove_weight_norm(self) -> None:
         for layer in self.convs1:
@@ -108,14 +195,20 @@ class ResBlock1(nn.Module):
             layer.remove_weight_norm()
 
 
-class ResBlock2(nn.Module):
-    """layers.py:49-69 — 2 x [lrelu -> conv(k, d_i) -> + x]."""
+class ResBlock2(_ResBlockBase):
+    """layers.py:49-69 - 2 x [lrelu -> conv(k, d_i) -> + x]."""
+
+    _kind = 2
 
     def __init__(self, channels: int, kernel_size: int = 3, dilation=(1, 3)) -> None:
         super().__init__()
         # the reference builds exactly two convs from dilation[0] and dilation[1] (layers.py:52-57)
         self.channels, self.kernel_size, self.dilation = channels, kernel_size, tuple(dilation)[:2]
         self.convs = nn.ModuleList([_WNConv(channels, channels, kernel_size) for _ in self.dilation])
+        self._rb_init()
+
+    def _rb_layers(self) -> List[tuple]:
+        return [("convs.%d" % m, l) for m, l in enumerate(self.convs)]
 
     def remove_weight_norm(self) -> None:
         for layer in self.convs:
@@ -298,6 +391,11 @@ class HifiGan(nn.Module):
         if self._handle is None:
             raise RuntimeError("call forward() once first")
         return int(_native.lib().e2e_voc_launches_per_forward(self._handle))
+
+    def last_forward_was_graph(self) -> bool:
+        """True if the last forward replayed a captured CUDA graph (same input / output / workspace buffers as a
+        previous call - what HostPipeline and `out=` loops do) instead of enqueueing its kernels one by one."""
+        return self._handle is not None and int(_native.lib().e2e_voc_last_forward_was_graph(self._handle)) == 1
 
     def _workspace(self, B: int, T: int, device: torch.device) -> torch.Tensor:
         key = (B, T, str(device))

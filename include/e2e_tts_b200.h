@@ -122,6 +122,27 @@ int e2e_voc_hop(const e2e_voc* v);
 /* Kernel launches enqueued by one e2e_voc_forward call at the current configuration. */
 int e2e_voc_launches_per_forward(const e2e_voc* v);
 
+/* A forward whose (B, T, input, output, workspace) combination has been seen before is captured into a CUDA graph
+ * the second time and replayed afterwards (serving loops that reuse their buffers; E2E_NO_GRAPH=1 disables it).
+ * Returns 1 if the handle's last forward was such a replay, 0 if it enqueued its kernels one by one. */
+int e2e_voc_last_forward_was_graph(const e2e_voc* v);
+
+/* ---- standalone residual blocks ----
+ * Replace ResBlock1.forward / ResBlock2.forward (e2e_tts/models/vocoder/layers.py:33-40, 60-65) as modules of their
+ * own (the generator runs the same convolutions through its fused launches).  kind: 1 = ResBlock1 (pairs of a dilated
+ * and an undilated conv), 2 = ResBlock2 (one dilated conv per step).  Layer names: "convs1.<m>", "convs2.<m>" (kind 1)
+ * or "convs.<m>" (kind 2), weights FOLDED fp32 [C][C][k] on the host as for e2e_voc_load_layer.  x: device fp32, element
+ * (b, c, t) at x[b*sB + c*sC + t*sT]; out: device fp32 [B][C][T] contiguous. */
+typedef struct e2e_resblock e2e_resblock;
+int e2e_resblock_create(int32_t kind, int32_t channels, int32_t kernel_size, const int32_t* dilations,
+                        int32_t n_dilations, e2e_resblock** out);
+void e2e_resblock_destroy(e2e_resblock* rb);
+int e2e_resblock_load_layer(e2e_resblock* rb, const char* name, const float* weight, int64_t weight_numel,
+                            const float* bias, int64_t bias_numel);
+size_t e2e_resblock_workspace_bytes(const e2e_resblock* rb, int32_t B, int32_t T);
+int e2e_resblock_forward(e2e_resblock* rb, const float* x, int64_t sB, int64_t sC, int64_t sT, int32_t B, int32_t T,
+                         float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- Postnet (N2, the step right before the vocoder) ----
  * Replaces Postnet.forward (e2e_tts/models/acoustic/unsupervised_fastspeech2/layers.py:507-563) in eval mode:
  * conv_layers x [Conv1d(kernel_size, same padding) -> BatchNorm1d -> tanh (all but the last)] on [B, T, n_channels].

@@ -228,6 +228,61 @@ def test_fp16_operand_mode_full_utterance_and_pcm():
         pkg.HifiGan(ho.DEFAULT_CONFIG, operand_dtype="fp8")
 
 
+def test_cuda_graph_replay_is_bit_identical_and_tracks_weight_reloads():
+    """A forward on buffers seen before is captured into a CUDA graph (2nd call) and replayed (3rd on): same bits as
+    the eager launches, a changed input buffer content is picked up (the graph reads the buffer, not a snapshot),
+    and new weights invalidate the captured graphs."""
+    voc, sd = build(ho.DEFAULT_CONFIG, 16, "strong")
+    mel_a, mel_b = mel_like(1, 60, 80).cuda(), mel_like(1, 60, 81).cuda()
+    buf = mel_a.clone()
+    out = torch.empty(1, 1, 60 * 256, device="cuda")
+    with torch.no_grad():
+        eager = voc(mel_a).clone()                       # fresh output buffer every call: never a graph
+        assert not voc.last_forward_was_graph()
+        for i in range(4):
+            voc(buf, out=out)
+            assert voc.last_forward_was_graph() == (i >= 1)
+            assert torch.equal(out, eager)
+        buf.copy_(mel_b)
+        voc(buf, out=out)
+        assert voc.last_forward_was_graph() and torch.equal(out, voc(mel_b))
+        sd2 = ho.make_state_dict(ho.DEFAULT_CONFIG, 17, "strong")
+        voc.load_state_dict(sd2)
+        voc(buf, out=out)
+        assert not voc.last_forward_was_graph()          # plans and graphs were dropped with the old weights
+        want = ho.hifigan_forward(sd2, ho.DEFAULT_CONFIG, mel_b.cpu())
+    check(out, want, "after reload")
+
+
+@pytest.mark.parametrize("kind,C,k,dil", [(1, 128, 3, (1, 3, 5)), (1, 32, 7, (1, 3, 5)), (2, 64, 5, (2, 6)), (1, 256, 11, (1, 3, 5))])
+def test_resblock_modules_are_callable(kind, C, k, dil):
+    """ResBlock1.forward / ResBlock2.forward (layers.py:33-40, 60-65) as standalone modules, against the same eager ops
+    the oracle uses; also on a non-contiguous input view."""
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    rb = (pkg.ResBlock1 if kind == 1 else pkg.ResBlock2)(C, k, dil).cuda()
+    for p in rb.parameters():                       # O(1) activations through the block
+        if p.dim() == 3 and p.shape[1] > 1:
+            p.data.mul_(2.0)
+    x = torch.randn(2, 300, C).transpose(1, 2)      # [B, C, T] view, like the generator's caller passes
+    with torch.no_grad():
+        got = rb(x.cuda()).cpu()
+        y = x.clone()
+        if kind == 1:
+            for c1, c2, d in zip(rb.convs1, rb.convs2, rb.dilation):
+                xt = F.conv1d(F.leaky_relu(y, 0.1), c1.folded_weight().cpu(), c1.bias.cpu(), dilation=d, padding=ho.get_padding(k, d))
+                xt = F.conv1d(F.leaky_relu(xt, 0.1), c2.folded_weight().cpu(), c2.bias.cpu(), padding=ho.get_padding(k, 1))
+                y = xt + y
+        else:
+            for c1, d in zip(rb.convs, rb.dilation):
+                xt = F.conv1d(F.leaky_relu(y, 0.1), c1.folded_weight().cpu(), c1.bias.cpu(), dilation=d, padding=ho.get_padding(k, d))
+                y = xt + y
+    assert got.shape == y.shape
+    check(got, y, "resblock%d C=%d k=%d" % (kind, C, k))
+    with pytest.raises(RuntimeError):
+        rb.cpu()(x)
+
+
 def test_host_pipeline_variable_batch_shapes():
     """Serving batches differ in B and T from one submit to the next (one <=300-symbol bucket per request,
     e2e_tts/src/api/utils.py:131-145): the pipeline must re-size its device buffers, also with a plain callable that has

@@ -24,42 +24,56 @@ def dft8(a):
     return out
 
 
+K1_OF = [0, 1, 4, 7, 2, 3, 6, 5]          # mel.cu k1_of(): k1 handled by threads with (thread >> 3) == h
+H_OF = [K1_OF.index(k) for k in range(8)]  # mel.cu h_of()
+
+
 def kernel_fft1024_real(xw):
-    """xw: 1024 windowed real samples -> X[0..512], following the kernel's thread/smem choreography."""
+    """xw: 1024 windowed real samples -> X[0..512], following the kernel's thread / shared-memory / shuffle
+    choreography: pass 1 -> shared memory -> pass 2 -> shared memory (same buffer) -> pass 3 -> partner shuffles."""
     tw = np.exp(-2j * np.pi * np.arange(1024) / 1024)                     # device twiddle table
     z = xw[0::2] + 1j * xw[1::2]                                           # 512 complex points
     S1 = np.zeros(8 * 72, complex)
-    S2 = np.zeros(8 * 72, complex)
-    S3 = np.zeros(512 + 64, complex)
     for n2 in range(64):                                                   # pass 1: thread n2
         y = dft8([z[64 * n1 + n2] for n1 in range(8)])
         for k1 in range(8):
             S1[k1 * 72 + n2] = y[k1] * tw[2 * ((n2 * k1) % 512)]           # W_512^(n2*k1)
-    for t in range(64):                                                    # pass 2: thread (k1, b)
-        k1, b = t // 8, t % 8
+    regs = [[0j] * 8 for _ in range(64)]
+    S2 = np.zeros(8 * 72, complex)                                         # the same buffer, after a group barrier
+    for t in range(64):                                                    # pass 2: thread (h, b), k1 = K1_OF[h]
+        h, b = t // 8, t % 8
+        k1 = K1_OF[h]
         u = dft8([S1[k1 * 72 + 8 * a + b] for a in range(8)])
         for c in range(8):
-            S2[k1 * 72 + c * 9 + b] = u[c] * tw[16 * ((b * c) % 64)]       # W_64^(b*c)
-    for t in range(64):                                                    # pass 3: thread (k1, c)
-        k1, c = t // 8, t % 8
-        v = dft8([S2[k1 * 72 + c * 9 + b] for b in range(8)])
-        for d in range(8):
-            k = k1 + 8 * c + 64 * d
-            S3[k ^ ((k >> 3) & 7)] = v[d]
+            S2[h * 72 + c * 9 + b] = u[c] * tw[16 * ((b * c) % 64)]        # W_64^(b*c): U[k1][c][b]
+    for t in range(64):                                                    # pass 3: thread (h, c): regs[t][d] = Z[k1+8c+64d]
+        h, c = t // 8, t % 8
+        regs[t] = dft8([S2[h * 72 + c * 9 + b] for b in range(8)])
     X = np.zeros(513, complex)
-    for t in range(64):                                # post pass: thread t, bin pairs (k, 512 - k), k = t + 64 j
-        for j in range(4):
-            k = t + 64 * j
-            kk = (512 - k) % 512
-            a, bq = S3[k ^ ((k >> 3) & 7)], np.conj(S3[kk ^ ((kk >> 3) & 7)])
-            ze, zo = (a + bq) / 2, (a - bq) / 2j
-            wz = tw[k] * zo
-            X[k] = ze + wz
-            X[512 - k] = np.conj(ze - wz)
-    z = S3[256]                                        # thread 0: bin 256 (only |X| is used by the kernel)
-    X[256] = np.conj(z)
+    w16 = np.exp(-2j * np.pi * np.arange(8) / 16)
+    for t in range(64):                                                    # recombination with the partner thread
+        h, c = t // 8, t % 8
+        k1 = K1_OF[h]
+        if k1 == 0 and c == 0:
+            for d in range(8):
+                za, zb = regs[t][d], np.conj(regs[t][(8 - d) % 8])
+                ze, zo = (za + zb) / 2, (za - zb) / 2j
+                X[64 * d] = ze + w16[d] * zo
+                if d == 0:
+                    X[512] = ze - w16[d] * zo
+            continue
+        k1p, cp = (8 - k1) % 8, (7 - c) if k1 else (8 - c) % 8
+        hp = H_OF[k1p]
+        assert hp // 4 == h // 4, "partner threads must share a warp"
+        lane_p = 8 * (hp % 4) + cp
+        tp = 32 * (t // 32) + lane_p
+        wbase = tw[k1 + 8 * c]
+        for dd in range(8):
+            d = 7 - dd
+            za, zb = regs[t][d], np.conj(regs[tp][dd])
+            ze, zo = (za + zb) / 2, (za - zb) / 2j
+            X[k1 + 8 * c + 64 * d] = ze + wbase * w16[d] * zo
     return X
-
 
 def test_dft8_butterfly():
     rng = np.random.default_rng(0)
@@ -74,12 +88,38 @@ def test_fft_choreography_matches_rfft():
         np.testing.assert_allclose(kernel_fft1024_real(x), np.fft.rfft(x), atol=1e-10)
 
 
-def test_smem_maps_are_injective():
+def test_smem_maps_are_injective_and_conflict_free():
     s1 = {k1 * 72 + n2 for k1 in range(8) for n2 in range(64)}
-    s2 = {k1 * 72 + c * 9 + b for k1 in range(8) for c in range(8) for b in range(8)}
-    s3 = {k ^ ((k >> 3) & 7) for k in range(512)}
-    assert len(s1) == 512 and len(s2) == 512 and len(s3) == 512
-    assert max(s1) < 576 and max(s2) < 576 and max(s3) < 576
+    s2 = {h * 72 + c * 9 + b for h in range(8) for c in range(8) for b in range(8)}
+    assert len(s1) == 512 and max(s1) < 576 and len(s2) == 512 and max(s2) < 576
+    # pass 2 reads S1[k1 * 72 + 8 q + lo] as 8-byte words: a half-warp (16 lanes = two h values) must hit 16 distinct
+    # bank pairs for every q (the k1 permutation keeps the two rows an odd number of rows apart)
+    for half in range(4):
+        for q in range(8):
+            banks = {((K1_OF[2 * half + hh] * 72 + 8 * q + lo) * 2) % 32 for hh in range(2) for lo in range(8)}
+            assert len(banks) == 16
+    # magnitude stores mag[k], k = k1 + 8 c + 64 d, for the 32 lanes of a warp and a fixed d: at most 2-way (c and c + 4
+    # share a bank: 16 distinct banks, 8 such stores per frame and warp)
+    for w in range(2):
+        for d in range(8):
+            banks = [(K1_OF[4 * w + hh] + 8 * c + 64 * d) % 32 for hh in range(4) for c in range(8)]
+            assert len(set(banks)) == 16 and max(banks.count(x) for x in set(banks)) == 2
+
+
+def test_partner_threads_share_a_warp_and_cover_every_bin():
+    seen = set()
+    for t in range(64):
+        h, c = t // 8, t % 8
+        k1 = K1_OF[h]
+        k1p = (8 - k1) % 8
+        assert H_OF[k1p] // 4 == h // 4
+        for d in range(8):
+            seen.add(k1 + 8 * c + 64 * d)
+    assert seen == set(range(512))
+    assert sorted(K1_OF) == list(range(8)) and all(K1_OF[H_OF[k]] == k for k in range(8))
+    # the packed tables in mel.cu
+    assert [(0x56327410 >> (4 * h)) & 7 for h in range(8)] == K1_OF
+    assert [(0x36725410 >> (4 * k)) & 7 for k in range(8)] == H_OF
 
 
 def test_parseval_energy_identity():
@@ -93,33 +133,26 @@ def test_parseval_energy_identity():
         np.testing.assert_allclose(lhs, rhs, rtol=1e-12)
 
 
-def test_filterbank_block_form_is_exact_and_fits():
-    """Mirror of e2e_mel_create's sparse filterbank (mel.cu): thread t of a frame owns bins [6t, 6t + 6) and the filters
-    overlapping them as a dense 5 x 6 block; one partial per (filter, thread); fixed-order sums reproduce basis @ mag.
-    Checks the bounds the kernel variant <BPT = 6, FPB = 5> relies on for the e2e-tts basis."""
+def test_filterbank_span_form_is_exact():
+    """Mirror of e2e_mel_create's sparse filterbank (mel.cu): per filter the span [lo, hi] of its non-zero bins with
+    the weights packed back to back; the kernel's per-(filter, frame) dot product over the span reproduces basis @ mag.
+    The magnitude tile has an odd row pitch, so the 32 lanes (frames) of a warp read 32 distinct banks."""
     from oracle import mel_oracle as mo
     basis = mo.slaney_mel_basis().astype(np.float64)
     n_mels, nbins = basis.shape
-    nb = 1 + max(k for k in range(nbins) if basis[:, k].any())
-    assert nb == 372 and 64 * 6 >= nb                      # bins the kernel computes magnitudes for
-    BPT, FPB = 6, 5
+    lo = [int(np.nonzero(basis[r])[0][0]) for r in range(n_mels)]
+    hi = [int(np.nonzero(basis[r])[0][-1]) for r in range(n_mels)]
+    nb = 1 + max(hi)
+    assert nb == 372
+    off, wpk = [], []
+    for r in range(n_mels):
+        off.append(len(wpk))
+        wpk.extend(basis[r, lo[r]: hi[r] + 1])
+    assert len(wpk) <= 1024                                # a few KB of shared memory per CTA
     rng = np.random.default_rng(3)
     mag = rng.uniform(0, 10, nbins)
-    first, count, part = {}, {}, {}
-    for t in range(64):
-        bins = [k for k in range(t * BPT, (t + 1) * BPT) if k < nbins]
-        filt = [r for r in range(n_mels) if basis[r, bins].any()]
-        assert len(filt) <= FPB
-        for r in filt:
-            first.setdefault(r, t)
-            count[r] = t - first[r] + 1
-            part[(r, t - first[r])] = sum(basis[r, k] * mag[k] for k in bins)
-    split = max(count.values())
-    assert split <= 12
-    got = np.array([sum(part.get((r, q), 0.0) for q in range(split)) for r in range(n_mels)])
+    got = np.array([sum(wpk[off[r] + i] * mag[lo[r] + i] for i in range(hi[r] - lo[r] + 1)) for r in range(n_mels)])
     np.testing.assert_allclose(got, basis @ mag, rtol=1e-12)
-    # padded magnitude index: pitch 7 per 6-bin block keeps the 64 threads on distinct banks
-    pad = lambda k: k + (k // BPT) * ((BPT | 1) - BPT)
-    assert len({pad(k) for k in range(384)}) == 384 and max(pad(k) for k in range(384)) < 584
-    for i in range(BPT):
-        assert len({(t * 7 + i) % 32 for t in range(32)}) == 32
+    magp = nb | 1
+    for k in (0, 5, 371):
+        assert len({(f * magp + k) % 32 for f in range(32)}) == 32
