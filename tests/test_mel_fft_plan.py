@@ -136,7 +136,7 @@ def test_parseval_energy_identity():
 def test_filterbank_span_form_is_exact():
     """Mirror of e2e_mel_create's sparse filterbank (mel.cu): per filter the span [lo, hi] of its non-zero bins with
     the weights packed back to back; the kernel's per-(filter, frame) dot product over the span reproduces basis @ mag.
-    The magnitude tile has an odd row pitch, so the 32 lanes (frames) of a warp read 32 distinct banks."""
+    The magnitude tile's rows are whole float4s with a pitch of 4 x odd words (conflict-free 128-bit lane reads)."""
     from oracle import mel_oracle as mo
     basis = mo.slaney_mel_basis().astype(np.float64)
     n_mels, nbins = basis.shape
@@ -153,6 +153,13 @@ def test_filterbank_span_form_is_exact():
     mag = rng.uniform(0, 10, nbins)
     got = np.array([sum(wpk[off[r] + i] * mag[lo[r] + i] for i in range(hi[r] - lo[r] + 1)) for r in range(n_mels)])
     np.testing.assert_allclose(got, basis @ mag, rtol=1e-12)
-    magp = nb | 1
-    for k in (0, 5, 371):
-        assert len({(f * magp + k) % 32 for f in range(32)}) == 32
+    # rows are whole float4s, pitch = 4 x odd: the 8 lanes (frames) of a quarter warp read 8 distinct 16-byte bank groups
+    magp = (((nb + 3) // 4) | 1) * 4
+    assert magp >= nb and (magp // 4) % 2 == 1
+    for k4 in (0, 5, 92):
+        for q in range(4):
+            assert len({(f * (magp // 4) + k4) % 8 for f in range(8 * q, 8 * q + 8)}) == 8
+    # spans widened to whole groups of four bins stay inside a row
+    for r in range(n_mels):
+        lo4 = lo[r] & ~3
+        assert lo4 + (hi[r] + 1 - lo4 + 3) // 4 * 4 <= magp
