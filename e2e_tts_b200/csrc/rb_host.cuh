@@ -25,11 +25,11 @@ inline int rb_halo(int k, const int* dil, int n_pairs) {
 
 // The fused chain needs per lane TMEM acc + x of 128*MT x C fp32 each (two lanes: 4 * MT * C = 512 columns) and two
 // slabs per lane: C in {32, 64, 128} with MT = 128 / C.  It recomputes the halo at both ends of every unit, so it is
-// used where the halo is a small part of the unit (>= 75 % of the computed rows stored) and the chain measured faster
-// than its three pair launches (B200, 16 x 5 s, k = 3, d = 1/3/5; profiles/r02_rb_fusion.md): C = 64 213 vs 243 us,
-// C = 32 187 vs 202 us, but C = 128 320 vs 302 us (one 128-row tile per unit: 19 % of the rows are halo and the
-// epilogues - the bound of every k = 3 launch - do not get cheaper), so C = 128 keeps the pair kernels.
-// E2E_RB_FUSION=0 disables the fused chain, =2 forces it wherever it fits.
+// used where the chain measured faster than its three pair launches (B200, 16 x 5 s, d = 1/3/5;
+// profiles/r02_experiments_notes.md §3): k = 3 at C = 64 (213 vs 243 us) and C = 32 (187 vs 202 us).  Those pair launches
+// are epilogue-bound and the 12-row halo is cheap.  Not at C = 128 (320 vs 302 us: one 128-row tile per unit, 19 % halo
+// rows) and not for k >= 5: there the launches are MMA-bound, so every halo row costs (C = 32: k = 7 343 vs 307 us,
+// k = 11 551 vs 375 us; C = 64, k = 7: 435 vs 351 us).  E2E_RB_FUSION=0 disables the fused chain, =2 forces it wherever it fits.
 inline bool rb_supported(int C, int k, const int* dil, int n_pairs) {
   static const char* e = std::getenv("E2E_RB_FUSION");
   if (e && e[0] == '0') return false;
@@ -41,7 +41,7 @@ inline bool rb_supported(int C, int k, const int* dil, int n_pairs) {
   const int r_out = 128 * mt - 2 * rb_halo(k, dil, n_pairs);
   if (r_out < 32) return false;
   if (e && e[0] == '2') return true;
-  return C <= 64 && r_out * 4 >= 128 * mt * 3;
+  return C <= 64 && k <= 3;
 }
 
 inline int plan_rb(RbPlan& plan, int C, int k, const int* dil, int n_pairs, int B, int T, int n_sms = 148) {

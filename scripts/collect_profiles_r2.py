@@ -1,0 +1,55 @@
+"""Round 2 (profiles/r02_*).  Turns the files scripts/gpu_r2_profile.sh left in gpurun_out/ into the committed evidence under profiles/:
+    python scripts/collect_profiles_r2.py a
+per-launch time + DRAM table, roofline_traffic.json (read by bench.py), ncu --set full summaries, bench lines, logs."""
+import csv, json, os, shutil, subprocess, sys
+
+tag = sys.argv[1]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+lines = [l for l in open(os.path.join(G, "launches_%s.csv" % tag)) if l.startswith('"')]
+by, order = {}, []
+for r in csv.DictReader(lines):
+    i = r["ID"]
+    if i not in by:
+        by[i] = {"name": r["Kernel Name"], "grid": r["Grid Size"]}
+        order.append(i)
+    by[i][r["Metric Name"]] = float(r["Metric Value"])
+    by[i][r["Metric Name"] + "_u"] = r["Metric Unit"]
+ids = [i for i in order if "mel_to_act" in by[i]["name"]]
+fw = order[order.index(ids[1]):order.index(ids[2])]
+mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+tot_t = tot_b = tc_b = tc_t = 0.0
+out = []
+for k, i in enumerate(fw):
+    d = by[i]
+    t = d["gpu__time_duration.sum"] / 1e3
+    rb = d["dram__bytes_read.sum"] * mult[d["dram__bytes_read.sum_u"]]
+    wb = d["dram__bytes_write.sum"] * mult[d["dram__bytes_write.sum_u"]]
+    n = d["name"].split("(")[0].split("::")[-1][:30]
+    out.append("%3d %-30s grid=%-14s %8.1f us  dram rd %7.1f MB  wr %7.1f MB" % (k, n, d["grid"], t, rb / 1e6, wb / 1e6))
+    tot_t += t
+    tot_b += rb + wb
+    if "tc_kernel" in n:   # conv_tc / pair_tc / rb_tc
+        tc_b += rb + wb
+        tc_t += t
+hdr = ("forward #1 of `python bench.py --steps 1 --warmup 3 --passes 1 --quick --no-side` under ncu (serialised, cold-cache, no "
+       "programmatic overlap: compare shares): %d launches, %.1f us, DRAM %.1f MB; tcgen05 launches: %.1f us, DRAM %.1f MB"
+       % (len(fw), tot_t, tot_b / 1e6, tc_t, tc_b / 1e6))
+name = "r02_launches_%s_time_dram.txt" % tag
+open(os.path.join(P, name), "w").write(hdr + "\n" + "\n".join(out) + "\n")
+json.dump({"dram_bytes_per_step_tcgen05": tc_b, "dram_bytes_per_step_all": tot_b,
+           "source": "profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, one forward)" % name},
+          open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
+print(hdr)
+for src, dst in (("pair_s1k11", "pair_s1k11"), ("rb_s2k3", "rb_s2k3"), ("mel", "mel")):
+    rep = os.path.join(G, "prof_%s_%s.ncu-rep" % (src, tag))
+    if os.path.exists(rep):
+        txt = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep, "14"],
+                             capture_output=True, text=True).stdout
+        open(os.path.join(P, "r02_ncu_full_%s_%s.txt" % (dst, tag)), "w").write(txt)
+for src, dst in (("bench_%s.json", "r02_bench_%s.json"), ("bench_ref_%s.json", "r02_bench_reference_%s.json"),
+                 ("bench_fp16_%s.json", "r02_bench_fp16_operands_%s.json"), ("pytest_gpu_%s.log", "r02_pytest_gpu_%s.log"),
+                 ("parity_margins_%s.jsonl", "r02_parity_margins_%s.jsonl")):
+    if os.path.exists(os.path.join(G, src % tag)):
+        shutil.copy(os.path.join(G, src % tag), os.path.join(P, dst % tag))
