@@ -73,6 +73,7 @@ class _MelHandle:
         _native.check(rc, "e2e_mel_create")
         self.h = h
         self.n_mels = n_mels
+        self.n_fft, self.hop = int(n_fft), int(hop)
 
     def num_frames(self, L: int) -> int:
         return int(_native.lib().e2e_mel_num_frames(self.h, L))
@@ -81,7 +82,8 @@ class _MelHandle:
         B, L = wav.shape
         T = self.num_frames(L)
         if T < 1:
-            raise ValueError("input too short: need more than %d samples" % 384)
+            raise ValueError("input too short: need more than %d samples (the reflect padding, (n_fft - hop) / 2)"
+                             % ((self.n_fft - self.hop) // 2))
         dev = wav.device
         mel = torch.empty((B, self.n_mels, T), dtype=torch.float32, device=dev)
         energy = torch.empty((B, T), dtype=torch.float32, device=dev) if want_energy else None
