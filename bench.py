@@ -52,7 +52,7 @@ FLOP_PER_FRAME = 614105088          # 2*MACs of all 78 convs p
 CONV_TC_FLOP_PER_FRAME = FLOP_PER_FRAME - 114688   # everything but conv_post runs on the tensor cores
 MEL_L = 220500           # 10 s clip
 MEL_CLIPS = 1024
-MEL_WARP_INSTR_PER_FRAME = 1207   # ncu, profiles/r02_ncu_full_mel_a.txt
+MEL_WARP_INSTR_PER_FRAME = 1147   # ncu smsp__inst_executed.sum / 881 664 frames, profiles/r02_ncu_full_mel_c.txt
 METRIC = "audio_seconds_synthesized_per_second"
 UNIT = "audio-s/s"
 NUMERICS = ("bf16 operands / fp32 accumulate; activations stored once as bf16 leaky_relu(x); residual adds and the "
@@ -244,6 +244,81 @@ def run_reference(args):
     }))
 
 
+def cfg1_cpu_reference():
+    """SURVEY.md §8 d2 / BASELINE config 1: single-utterance inference on the CPU exactly as the reference runs it -
+    the reference class with its constructor's default init (torch.manual_seed(1234)), weight-norm hooks left on
+    (e2e_tts/src/api/utils.py:53-56), input torch.randn(1, 80, 431), fp32, all host threads."""
+    from e2e_tts_b200 import synthetic as sy
+    from oracle import ref_loader
+    cls = ref_loader.reference_hifigan_class()
+    if cls is None:
+        return {"unavailable": "baseline/_ref not staged"}
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(1234)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = cls(sy.DEFAULT_CONFIG).eval()
+        x = torch.randn(1, 80, T_FRAMES)
+        times = []
+        with torch.no_grad():
+            for i in range(8):
+                t0 = time.perf_counter()
+                m(x)
+                if i >= 3:
+                    times.append(time.perf_counter() - t0)
+    times.sort()
+    audio_s = T_FRAMES * HOP / SR
+    return {"workload": "1 utterance x 5 s on the CPU, reference HifiGan, default init, weight-norm hooks on",
+            "cores": cores, "kind": "reference", "best_s": times[0], "median_s": times[len(times) // 2],
+            "value": audio_s / times[0], "unit": UNIT}
+
+
+def mel_reference_baselines(dev, quick: bool):
+    """the reference TorchSTFT (baseline/_ref; librosa's filterbank = the restated algorithm) on the CPU
+    - per clip as e2e_tts/src/tools/tools_for_data.py:143-178 loops, and batched x 64 - and in eager PyTorch on the GPU."""
+    from oracle import ref_loader
+    cls = ref_loader.reference_stft_class()
+    if cls is None:
+        return {"unavailable": "baseline/_ref not staged"}
+    out = {"kind": "reference", "unit": UNIT}
+    g = torch.Generator().manual_seed(0)
+    clips = torch.rand(64, MEL_L, generator=g) * 2 - 1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        cpu = cls()
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu.mel_spectrogram(clips[:1], return_energy=True)
+        n = 4 if quick else 16
+        t0 = time.perf_counter()
+        for i in range(n):
+            cpu.mel_spectrogram(clips[i:i + 1], return_energy=True)
+        dt = time.perf_counter() - t0
+        out["cpu_per_clip"] = {"value": n * MEL_L / SR / dt, "ms_per_clip": dt / n * 1e3, "cores": os.cpu_count() or 1}
+        t0 = time.perf_counter()
+        cpu.mel_spectrogram(clips, return_energy=True)
+        dt = time.perf_counter() - t0
+        out["cpu_batched_64"] = {"value": 64 * MEL_L / SR / dt, "ms_per_clip": dt / 64 * 1e3}
+        try:
+            gpu = cls(device=str(dev)).to(dev)
+            xb = clips.to(dev)
+            for _ in range(2):
+                gpu.mel_spectrogram(xb, return_energy=True)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                gpu.mel_spectrogram(xb, return_energy=True)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            out["gpu_eager_batched_64"] = {"value": 64 * MEL_L / SR / (ms * 1e-3), "ms_per_64_clips": ms,
+                                           "note": "includes the reference's host-synchronising range assert"}
+        except Exception as e:
+            out["gpu_eager_batched_64"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    return out
+
+
 def gpu_eager_baseline(dev, quick: bool):
     """the reference modules in eager PyTorch on this same B200 (cuDNN, cudnn.benchmark on)."""
     from e2e_tts_b200 import synthetic as sy
@@ -353,8 +428,8 @@ def side_workloads(voc, dev, peaks, quick: bool):
     Tm = mel.shape[-1]
     alg = clips * (4 * MEL_L + 4 * 81 * Tm)          # fp32 audio in, fp32 mel (80) + energy (1) out
     gbs = alg / (ms * 1e-3) * 1e-9
-    # What bounds the kernel is instruction issue, not HBM: 1 207 warp instructions per frame
-    # (ncu smsp__inst_executed.sum / frames, profiles/r02_ncu_full_mel_*.txt) at 4 issue slots per cycle and SM
+    # What bounds the kernel is instruction issue, not HBM: 1 147 warp instructions per frame
+    # (ncu smsp__inst_executed.sum / frames, profiles/r02_ncu_full_mel_c.txt) at 4 issue slots per cycle and SM
     issue_floor_ms = clips * Tm * MEL_WARP_INSTR_PER_FRAME / (148 * 4 * 1.965e9) * 1e3
     w["cfg5_mel"] = {"workload": "%d clips x 10 s (L=220500 -> T=%d frames), TorchSTFT.mel_spectrogram(return_energy=True), "
                                  "range check off (no host sync)" % (clips, Tm),
@@ -364,7 +439,7 @@ def side_workloads(voc, dev, peaks, quick: bool):
                                   "algorithmic_bytes": alg, "hbm_floor_ms": alg / (peaks["hbm"] * 1e9) * 1e3,
                                   "issue_slot_floor_ms": issue_floor_ms, "issue_slot_frac": issue_floor_ms / ms,
                                   "note": "SURVEY.md §8 d7 names HBM as this path's roofline and `frac` is reported against it; "
-                                          "the kernel is bound by instruction issue (1207 warp instructions per frame, ncu): "
+                                          "the kernel is bound by instruction issue (1147 warp instructions per frame, ncu): "
                                           "issue_slot_frac = time at 100 % issue-slot use / measured time",
                                   "peak_source": peaks["source"]}}
     del wav, mel, en
@@ -622,6 +697,12 @@ def main():
             line["workloads"] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
         if not args.quick:
             line["gpu_eager_baseline"] = gpu_eager_baseline(dev, args.quick)
+            for key, fn in (("cfg1_cpu_reference", cfg1_cpu_reference),
+                            ("cfg5_mel_reference", lambda: mel_reference_baselines(dev, args.quick))):
+                try:
+                    line["workloads"][key] = fn()
+                except Exception as e:   # a baseline leg must never take the bench line down
+                    line["workloads"][key] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.quick:
         v, cores, kind, sample = cpu_reference_throughput(12.0, 2)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}

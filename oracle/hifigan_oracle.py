@@ -143,6 +143,8 @@ def hifigan_forward(sd: dict, config: dict, mel: torch.Tensor, dtype=torch.float
     x = _trunk(sd, config, mel, dtype, taps)
     x = F.leaky_relu(x)                                                                 # :49 (slope 0.01)
     x = F.conv1d(x, _weight(sd, "conv_post", dtype), sd["conv_post.bias"].to(dtype), padding=3)   # :50
+    if taps is not None:
+        taps["conv_post"] = x
     return torch.tanh(x)                                                                # :51
 
 
@@ -215,6 +217,8 @@ def _trunk(sd: dict, config: dict, mel: torch.Tensor, dtype, taps: Optional[dict
                     xt = F.leaky_relu(y, LRELU_SLOPE)
                     xt = F.conv1d(xt, _weight(sd, p1, dtype), b(p1), dilation=dil[m], padding=get_padding(ks, dil[m]))
                     y = xt + y
+            if taps is not None:
+                taps["resblocks.%d" % n] = y
             xs = y if xs is None else xs + y
         x = xs / nk                                                                     # :48
         if taps is not None:

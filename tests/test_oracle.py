@@ -142,3 +142,22 @@ def test_istft_selects_resblock2_for_the_shipped_int_config():
     assert "resblocks.0.convs.1" in names and "resblocks.0.convs1.0" not in names and len(names) == 16
     cfg = dict(ho.ISTFT_CONFIG, resblock="1")
     assert "resblocks.0.convs1.2" in [n for n, *_ in ho.layer_names(cfg)]
+
+
+def test_oracle_intermediates_against_reference_hooks():
+    """per-layer goldens.  tests/golden/voc_taps_strong.npz holds the outputs of forward hooks on the
+    UNMODIFIED reference generator's conv_pre, ups[i], resblocks[n] and conv_post (oracle/make_golden_taps.py); the
+    oracle's named intermediates must match them layer by layer."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voc_taps_strong.npz"))
+    sd = ho.make_state_dict(ho.DEFAULT_CONFIG, int(g["seed"]), "strong")
+    taps = {}
+    with torch.no_grad():
+        wav = ho.hifigan_forward(sd, ho.DEFAULT_CONFIG, torch.from_numpy(g["mel"]), taps=taps)
+    assert (wav - torch.from_numpy(g["wav"])).abs().max().item() <= 1e-5
+    names = [k[4:] for k in g.files if k.startswith("tap:")]
+    assert len(names) == 1 + 4 + 12 + 1
+    for n in names:
+        ref = torch.from_numpy(g["tap:" + n])
+        assert taps[n].shape == ref.shape, n
+        assert (taps[n] - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item()), n
