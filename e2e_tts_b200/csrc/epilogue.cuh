@@ -75,12 +75,13 @@ struct EpiOut {
   int f16;                  // 16-bit tensors (residual, running sum, out_act) are fp16 instead of bf16 (ptx.cuh pack16)
 };
 
-__device__ __forceinline__ void add_bf16x16(float (&f)[16], const uint4 (&q)[2], int f16) {
+template <bool F16>
+__device__ __forceinline__ void add_bf16x16(float (&f)[16], const uint4 (&q)[2]) {
   const uint32_t w[8] = {q[0].x, q[0].y, q[0].z, q[0].w, q[1].x, q[1].y, q[1].z, q[1].w};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float lo, hi;
-    unpack16(w[j], lo, hi, f16);
+    unpack16t<F16>(w[j], lo, hi);
     f[2 * j] += lo;
     f[2 * j + 1] += hi;
   }
@@ -103,14 +104,15 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // acc + bias + residual (+ partial sums) (* scale) -> leaky_relu -> 16 bf16 (8 packed words), for one 16-column item:
 // the arithmetic of epi_finish16 without the stores (the fused pair kernel stages the result in shared memory and
 // writes it to global memory with coalesced accesses).
-__device__ __forceinline__ void epi_compute16(const uint32_t (&v)[16], const float4 (&bv)[4], const uint4 (&rq)[2],
-                                              const uint4 (&sa)[2], const EpiOut& o, uint32_t (&pk)[8]) {
+template <bool F16>
+__device__ __forceinline__ void epi_compute16_t(const uint32_t (&v)[16], const float4 (&bv)[4], const uint4 (&rq)[2],
+                                                const uint4 (&sa)[2], const EpiOut& o, uint32_t (&pk)[8]) {
   float f[16];
   const uint32_t w[8] = {rq[0].x, rq[0].y, rq[0].z, rq[0].w, rq[1].x, rq[1].y, rq[1].z, rq[1].w};
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float lo, hi;
-    unpack16(w[j], lo, hi, o.f16);
+    unpack16t<F16>(w[j], lo, hi);
     f[2 * j] = fminf(lo, lo * o.inv);
     f[2 * j + 1] = fminf(hi, hi * o.inv);
   }
@@ -121,7 +123,7 @@ __device__ __forceinline__ void epi_compute16(const uint32_t (&v)[16], const flo
     f[4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bv[i].z;
     f[4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bv[i].w;
   }
-  if (o.sum_a) add_bf16x16(f, sa, o.f16);
+  if (o.sum_a) add_bf16x16<F16>(f, sa);
   if (o.scale != 0.f) {
     const float sc = o.scale;
 #pragma unroll
@@ -131,15 +133,21 @@ __device__ __forceinline__ void epi_compute16(const uint32_t (&v)[16], const flo
   if (o.act_tanh) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      pk[i] = pack16(tanhf(f[2 * i]), tanhf(f[2 * i + 1]), o.f16);
+      pk[i] = pack16t<F16>(tanhf(f[2 * i]), tanhf(f[2 * i + 1]));
     }
     return;
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float a = f[2 * i], c = f[2 * i + 1];
-    pk[i] = pack16(fmaxf(a, a * s), fmaxf(c, c * s), o.f16);  // leaky_relu, 0 < s <= 1
+    pk[i] = pack16t<F16>(fmaxf(a, a * s), fmaxf(c, c * s));  // leaky_relu, 0 < s <= 1
   }
+}
+
+__device__ __forceinline__ void epi_compute16(const uint32_t (&v)[16], const float4 (&bv)[4], const uint4 (&rq)[2],
+                                              const uint4 (&sa)[2], const EpiOut& o, uint32_t (&pk)[8]) {
+  if (o.f16) epi_compute16_t<true>(v, bv, rq, sa, o, pk);
+  else epi_compute16_t<false>(v, bv, rq, sa, o, pk);
 }
 
 // acc + bias + residual (+ partial sums) (* scale) -> out_f32 and/or leaky_relu -> out_act, for one 16-column item.
@@ -148,8 +156,9 @@ __device__ __forceinline__ void epi_compute16(const uint32_t (&v)[16], const flo
 //   rq       residual: 16 bf16 (zeros when there is none)
 //   sa       running sum: 16 bf16 (only read when o.sum_a != nullptr)
 //   off      element offset of (row, first column) in the [B][T][n_total] outputs
-__device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const float4 (&bv)[4], const uint4 (&rq)[2],
-                                             const uint4 (&sa)[2], const EpiOut& o, size_t off, bool valid) {
+template <bool F16>
+__device__ __forceinline__ void epi_finish16_t(const uint32_t (&v)[16], const float4 (&bv)[4], const uint4 (&rq)[2],
+                                               const uint4 (&sa)[2], const EpiOut& o, size_t off, bool valid) {
   if (!valid) return;
   float f[16];
   const uint32_t w[8] = {rq[0].x, rq[0].y, rq[0].z, rq[0].w, rq[1].x, rq[1].y, rq[1].z, rq[1].w};
@@ -157,7 +166,7 @@ __device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const floa
   for (int j = 0; j < 8; ++j) {
     // bf16 -> fp32 is a 16-bit shift; x = min(a, a/slope) inverts leaky_relu for 0 < slope < 1
     float lo, hi;
-    unpack16(w[j], lo, hi, o.f16);
+    unpack16t<F16>(w[j], lo, hi);
     f[2 * j] = fminf(lo, lo * o.inv);
     f[2 * j + 1] = fminf(hi, hi * o.inv);
   }
@@ -168,7 +177,7 @@ __device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const floa
     f[4 * i + 2] += __uint_as_float(v[4 * i + 2]) + bv[i].z;
     f[4 * i + 3] += __uint_as_float(v[4 * i + 3]) + bv[i].w;
   }
-  if (o.sum_a) add_bf16x16(f, sa, o.f16);
+  if (o.sum_a) add_bf16x16<F16>(f, sa);
   if (o.scale != 0.f) {
     const float sc = o.scale;
 #pragma unroll
@@ -189,17 +198,23 @@ __device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const floa
     if (o.act_tanh) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        pk[i] = pack16(tanhf(f[2 * i]), tanhf(f[2 * i + 1]), o.f16);
+        pk[i] = pack16t<F16>(tanhf(f[2 * i]), tanhf(f[2 * i + 1]));
       }
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float a = f[2 * i], c = f[2 * i + 1];
-        pk[i] = pack16(fmaxf(a, a * s), fmaxf(c, c * s), o.f16);  // leaky_relu, 0 < s <= 1
+        pk[i] = pack16t<F16>(fmaxf(a, a * s), fmaxf(c, c * s));  // leaky_relu, 0 < s <= 1
       }
     }
     st_global_256(o.out_act + off, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));
   }
+}
+
+__device__ __forceinline__ void epi_finish16(const uint32_t (&v)[16], const float4 (&bv)[4], const uint4 (&rq)[2],
+                                             const uint4 (&sa)[2], const EpiOut& o, size_t off, bool valid) {
+  if (o.f16) epi_finish16_t<true>(v, bv, rq, sa, o, off, valid);
+  else epi_finish16_t<false>(v, bv, rq, sa, o, off, valid);
 }
 
 }  // namespace e2e

@@ -379,7 +379,9 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
     E2E_TR2_DECL
 
     // one 16-column item of c1: acc + bias1 -> leaky_relu -> bf16 -> M slab (zero outside the utterance)
-    auto store_mid = [&](const uint32_t (&v)[16], const float4 (&bv)[4], int m, int cc, int t0, uint8_t* mdst) {
+    auto store_mid_t = [&](auto f16tag, const uint32_t (&v)[16], const float4 (&bv)[4], int m, int cc, int t0,
+                           uint8_t* mdst) {
+      constexpr bool F16 = decltype(f16tag)::value;
       const int r = m * 128 + row_in_tile;   // M slab row
       const int t = t0 - h2 + r;             // global time step of this row
       const bool inside = t >= 0 && t < p.T;
@@ -388,8 +390,8 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       for (int i = 0; i < 4; ++i) {
         const float f0 = __uint_as_float(v[4 * i]) + bv[i].x, f1 = __uint_as_float(v[4 * i + 1]) + bv[i].y;
         const float f2 = __uint_as_float(v[4 * i + 2]) + bv[i].z, f3 = __uint_as_float(v[4 * i + 3]) + bv[i].w;
-        const uint32_t h0 = pack16(fmaxf(f0, f0 * smid), fmaxf(f1, f1 * smid), p.f16);
-        const uint32_t h1v = pack16(fmaxf(f2, f2 * smid), fmaxf(f3, f3 * smid), p.f16);
+        const uint32_t h0 = pack16t<F16>(fmaxf(f0, f0 * smid), fmaxf(f1, f1 * smid));
+        const uint32_t h1v = pack16t<F16>(fmaxf(f2, f2 * smid), fmaxf(f3, f3 * smid));
         pk[2 * i] = inside ? h0 : 0u;
         pk[2 * i + 1] = inside ? h1v : 0u;
       }
@@ -404,6 +406,10 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         off ^= ((off >> 7) & SWZ) << 4;
         *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       }
+    };
+    auto store_mid = [&](const uint32_t (&v)[16], const float4 (&bv)[4], int m, int cc, int t0, uint8_t* mdst) {
+      if (p.f16) store_mid_t(std::true_type{}, v, bv, m, cc, t0, mdst);
+      else store_mid_t(std::false_type{}, v, bv, m, cc, t0, mdst);
     };
     auto param_bias = [&](const float* sb, int cc, float4 (&bv)[4]) {
 #pragma unroll

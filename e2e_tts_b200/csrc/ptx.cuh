@@ -7,6 +7,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace e2e {
 
@@ -332,8 +333,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, i
 // The 16-bit operand format of the tensor-core path (activations in HBM / shared memory, packed weights): bf16 by
 // default, fp16 when the generator was created with operand_dtype = fp16.  Two values <-> one 32-bit word, first value in
 // the low half.  The fp16 conversion saturates to +-65504 instead of producing inf.
-__device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
-  if (f16) {
+// The format is a run-time property of the generator but uniform over a launch: the epilogues branch ONCE per
+// 16-column item into code specialised on it (a per-value `f16 ? a : b` costs a predicated-off instruction per value).
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16t(float a, float b) {
+  if (F16) {
     uint32_t r;
     asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
@@ -341,8 +345,9 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ void unpack16(uint32_t w, float& lo, float& hi, int f16) {
-  if (f16) {
+template <bool F16>
+__device__ __forceinline__ void unpack16t(uint32_t w, float& lo, float& hi) {
+  if (F16) {
     const float2 v = __half22float2(*reinterpret_cast<const __half2*>(&w));
     lo = v.x;
     hi = v.y;
@@ -350,6 +355,13 @@ __device__ __forceinline__ void unpack16(uint32_t w, float& lo, float& hi, int f
     lo = __uint_as_float(w << 16);   // bf16 -> fp32 is a 16-bit shift
     hi = __uint_as_float(w & 0xffff0000u);
   }
+}
+__device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
+  return f16 ? pack16t<true>(a, b) : pack16t<false>(a, b);
+}
+__device__ __forceinline__ void unpack16(uint32_t w, float& lo, float& hi, int f16) {
+  if (f16) unpack16t<true>(w, lo, hi);
+  else unpack16t<false>(w, lo, hi);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.

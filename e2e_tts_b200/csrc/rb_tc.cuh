@@ -292,19 +292,24 @@ rb_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ 
         bv[i] = make_float4(sb[cc * 16 + 4 * i], sb[cc * 16 + 4 * i + 1], sb[cc * 16 + 4 * i + 2], sb[cc * 16 + 4 * i + 3]);
     };
     // acc (or x) + bias -> leaky_relu -> bf16, zero outside the utterance -> 32 bytes of a slab row
-    auto act_store = [&](const uint32_t (&v)[16], const float4 (&bv)[4], bool inside, uint32_t dst) {
+    auto act_store_t = [&](auto f16tag, const uint32_t (&v)[16], const float4 (&bv)[4], bool inside, uint32_t dst) {
+      constexpr bool F16 = decltype(f16tag)::value;
       uint32_t pk[8];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float f0 = __uint_as_float(v[4 * i]) + bv[i].x, f1 = __uint_as_float(v[4 * i + 1]) + bv[i].y;
         const float f2 = __uint_as_float(v[4 * i + 2]) + bv[i].z, f3 = __uint_as_float(v[4 * i + 3]) + bv[i].w;
-        const uint32_t h0 = pack16(fmaxf(f0, f0 * smid), fmaxf(f1, f1 * smid), p.f16);
-        const uint32_t h1 = pack16(fmaxf(f2, f2 * smid), fmaxf(f3, f3 * smid), p.f16);
+        const uint32_t h0 = pack16t<F16>(fmaxf(f0, f0 * smid), fmaxf(f1, f1 * smid));
+        const uint32_t h1 = pack16t<F16>(fmaxf(f2, f2 * smid), fmaxf(f3, f3 * smid));
         pk[2 * i] = inside ? h0 : 0u;
         pk[2 * i + 1] = inside ? h1 : 0u;
       }
       st_shared_u4(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
       st_shared_u4(dst ^ 16u, make_uint4(pk[4], pk[5], pk[6], pk[7]));
+    };
+    auto act_store = [&](const uint32_t (&v)[16], const float4 (&bv)[4], bool inside, uint32_t dst) {
+      if (p.f16) act_store_t(std::true_type{}, v, bv, inside, dst);
+      else act_store_t(std::false_type{}, v, bv, inside, dst);
     };
     // x <- inverse leaky_relu of the stored input activation (16 bf16 of this thread's row) : seeds the TMEM residual
     auto seed = [&](uint32_t src, uint32_t taddr) {
