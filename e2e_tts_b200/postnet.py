@@ -129,6 +129,11 @@ class Postnet(nn.Module):
             _native.check(rc, "e2e_postnet_forward")
         return out
 
+    def __getstate__(self):
+        d = self.__dict__.copy()   # copies / pickles start without a native handle
+        d.update(_handle=None, _handle_device=None, _loaded_version=None, _workspaces={})
+        return d
+
     def __del__(self):
         try:
             if self._handle is not None:

@@ -144,6 +144,11 @@ class TorchSTFT(nn.Module):
         self.window = torch.hann_window(win_length).to(self.device)
         self._handles: Dict[str, _MelHandle] = {}
 
+    def __getstate__(self):
+        d = self.__dict__.copy()   # copies / pickles start without native handles
+        d["_handles"] = {}
+        return d
+
     def _handle(self, device: torch.device) -> _MelHandle:
         key = str(device)
         h = self._handles.get(key)

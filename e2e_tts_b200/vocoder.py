@@ -163,6 +163,12 @@ class _ResBlockBase(nn.Module):
             _native.check(rc, "e2e_resblock_forward")
         return out
 
+    def __getstate__(self):
+        # native handles belong to this instance: copies / pickles start without one and rebuild it on first use
+        d = self.__dict__.copy()
+        d.update(_rb_handle=None, _rb_device=None, _rb_version=None, _rb_ws={})
+        return d
+
     def __del__(self):
         try:
             if getattr(self, "_rb_handle", None) is not None:
@@ -481,6 +487,14 @@ class HifiGan(nn.Module):
                                                      ws.numel() - (ws_ptr - ws.data_ptr()), stream)
             _native.check(rc, "e2e_voc_forward_pcm16")
         return out
+
+    def __getstate__(self):
+        # the native handle (packed weights, plans, graphs) belongs to this instance: copy.deepcopy / pickle start
+        # without one and rebuild it on their first forward
+        d = self.__dict__.copy()
+        d.update(_handle=None, _handle_device=None, _loaded_version=None, _param_cache=None, _workspaces={},
+                 _profile_events=None)
+        return d
 
     def __del__(self):
         try:

@@ -118,3 +118,25 @@ def test_istft_generator_contract():
         g(torch.zeros(1, 80, 4))
     with pytest.raises(RuntimeError):
         pkg.inverse_stft(torch.zeros(1, 9, 5), torch.zeros(1, 9, 5), 16, 4, 16)
+
+
+def test_modules_copy_and_pickle_without_their_native_handles():
+    """copy.deepcopy / pickle of a module must not duplicate its native handle (double free): copies start without one."""
+    import copy
+    import pickle
+    import e2e_tts_b200 as pkg
+    from e2e_tts_b200 import synthetic as sy
+    voc = pkg.HifiGan(sy.DEFAULT_CONFIG)
+    voc._handle = 123                      # stand-in for a live e2e_voc*
+    try:
+        clone = copy.deepcopy(voc)
+        assert clone._handle is None and clone._workspaces == {} and voc._handle == 123
+        assert list(clone.state_dict()) == list(voc.state_dict())
+    finally:
+        voc._handle = None
+    stft = pkg.TorchSTFT()
+    stft._handles["cuda:0"] = object()
+    assert copy.deepcopy(stft)._handles == {}
+    stft._handles.clear()
+    rb = pickle.loads(pickle.dumps(pkg.ResBlock1(64)))
+    assert rb._rb_handle is None and len(rb.convs1) == 3
