@@ -25,11 +25,13 @@ inline int rb_halo(int k, const int* dil, int n_pairs) {
 
 // The fused chain needs per lane TMEM acc + x of 128*MT x C fp32 each (two lanes: 4 * MT * C = 512 columns) and two
 // slabs per lane: C in {32, 64, 128} with MT = 128 / C.  It recomputes the halo at both ends of every unit, so it is
-// used where the chain measured faster than its three pair launches (B200, 16 x 5 s, d = 1/3/5;
-// profiles/r02_experiments_notes.md §3): k = 3 at C = 64 (213 vs 243 us) and C = 32 (187 vs 202 us).  Those pair launches
-// are epilogue-bound and the 12-row halo is cheap.  Not at C = 128 (320 vs 302 us: one 128-row tile per unit, 19 % halo
-// rows) and not for k >= 5: there the launches are MMA-bound, so every halo row costs (C = 32: k = 7 343 vs 307 us,
-// k = 11 551 vs 375 us; C = 64, k = 7: 435 vs 351 us).  E2E_RB_FUSION=0 disables the fused chain, =2 forces it wherever it fits.
+// used where that is cheap: the k = 3 resblocks (H = 12 rows per side), whose pair launches are epilogue-bound.
+// Same-box A/B of the whole forward in the >= 2 s power-capped regime (16 x 5 s, ms per pass;
+// profiles/r02_experiments_notes.md §3): no fused chain 5.12, k = 3 at C <= 64 4.93, k = 3 at C <= 128 4.89 (the
+// default), + k = 7 at C <= 64 4.99-5.00, + k = 11 at C = 32 5.09: for k >= 7 the launches are MMA-bound and every
+// halo row costs.  (Isolated launches rank C = 128, k = 3 the other way round, 320 vs 302 us: the chain saves DRAM
+// traffic and launches, which the power-capped, PDL-overlapped forward rewards.)
+// E2E_RB_FUSION=0 disables the fused chain, =2 forces it wherever it fits; E2E_RB_KMAX / E2E_RB_CMAX move the rule.
 inline bool rb_supported(int C, int k, const int* dil, int n_pairs) {
   static const char* e = std::getenv("E2E_RB_FUSION");
   if (e && e[0] == '0') return false;
@@ -41,7 +43,10 @@ inline bool rb_supported(int C, int k, const int* dil, int n_pairs) {
   const int r_out = 128 * mt - 2 * rb_halo(k, dil, n_pairs);
   if (r_out < 32) return false;
   if (e && e[0] == '2') return true;
-  return C <= 64 && k <= 3;
+  static const char* ek = std::getenv("E2E_RB_KMAX");   // experiments: largest kernel size / channel count that is fused
+  static const char* ec = std::getenv("E2E_RB_CMAX");
+  const int kmax = ek ? atoi(ek) : 3, cmax = ec ? atoi(ec) : 128;
+  return C <= cmax && k <= kmax && r_out * 2 >= 128 * mt;
 }
 
 inline int plan_rb(RbPlan& plan, int C, int k, const int* dil, int n_pairs, int B, int T, int n_sms = 148) {
