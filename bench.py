@@ -52,7 +52,7 @@ FLOP_PER_FRAME = 614105088          # 2*MACs of all 78 convs p
 CONV_TC_FLOP_PER_FRAME = FLOP_PER_FRAME - 114688   # everything but conv_post runs on the tensor cores
 MEL_L = 220500           # 10 s clip
 MEL_CLIPS = 1024
-MEL_WARP_INSTR_PER_FRAME = 1147   # ncu smsp__inst_executed.sum / 881 664 frames, profiles/r02_ncu_full_mel_c.txt
+MEL_WARP_INSTR_PER_FRAME = 1147   # ncu smsp__inst_executed.sum / 881 664 frames, profiles/r02_ncu_full_mel_e.txt
 METRIC = "audio_seconds_synthesized_per_second"
 UNIT = "audio-s/s"
 NUMERICS = ("bf16 operands / fp32 accumulate; activations stored once as bf16 leaky_relu(x); residual adds and the "
@@ -434,7 +434,7 @@ def side_workloads(voc, dev, peaks, quick: bool):
     alg = clips * (4 * MEL_L + 4 * 81 * Tm)          # fp32 audio in, fp32 mel (80) + energy (1) out
     gbs = alg / (ms * 1e-3) * 1e-9
     # What bounds the kernel is instruction issue, not HBM: 1 147 warp instructions per frame
-    # (ncu smsp__inst_executed.sum / frames, profiles/r02_ncu_full_mel_c.txt) at 4 issue slots per cycle and SM
+    # (ncu smsp__inst_executed.sum / frames, profiles/r02_ncu_full_mel_e.txt) at 4 issue slots per cycle and SM
     issue_floor_ms = clips * Tm * MEL_WARP_INSTR_PER_FRAME / (148 * 4 * 1.965e9) * 1e3
     w["cfg5_mel"] = {"workload": "%d clips x 10 s (L=220500 -> T=%d frames), TorchSTFT.mel_spectrogram(return_energy=True), "
                                  "range check off (no host sync)" % (clips, Tm),

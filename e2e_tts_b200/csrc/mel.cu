@@ -9,7 +9,7 @@
 // overlap 4x); each group of 64 threads runs the 512-point complex FFT of an even/odd-packed frame as three radix-8
 // passes held in registers (8 complex values per thread, packed f32x2 arithmetic), exchanging through one padded,
 // conflict-free shared-memory buffer after passes 1 and 2.  What bounds the kernel is instruction issue (~700 instructions
-// per thread and frame in round 1: profiles/r02_mel_notes.md), so this version spends its changes on instruction count:
+// per thread and frame in round 1: profiles/r02_experiments_notes.md §7), so this version spends its changes on instruction count:
 //   * complex butterflies and twiddle multiplies in Blackwell's packed FP32 instructions (FADD2 / FMUL2 / FFMA2);
 //   * the real-FFT recombination pairs bin k with 512 - k.  With k = k1 + 8 c + 64 d held by thread (k1, c) in register d,
 //     512 - k lives in ONE other thread, (8 - k1, 7 - c) [(0, 8 - c) for k1 = 0], in register 7 - d: the k1 -> thread
@@ -66,7 +66,7 @@ __device__ __forceinline__ float sqrt_approx(float x) {  // one MUFU.SQRT: max r
 
 // Complex values travel as packed f32x2 register pairs (lo = re, hi = im) and the butterflies use Blackwell's packed
 // FP32 instructions (FADD2 / FMUL2 / FFMA2: one instruction per complex add, two per complex multiply) - the kernel
-// is bound by instruction issue, not by memory (profiles/r02_mel_notes.md).
+// is bound by instruction issue, not by memory (profiles/r02_experiments_notes.md §7).
 typedef unsigned long long c64;
 __device__ __forceinline__ c64 pk2(float lo, float hi) {
   c64 r;

@@ -16,8 +16,8 @@ E2E_OPERAND_DTYPE=fp16 timeout 600 python bench.py --quick --no-side > gpurun_ou
 CMD="python bench.py --steps 1 --warmup 3 --passes 1 --quick --no-side"
 $CMD > gpurun_out/ncu_plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 520 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_l.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:pair_tc -s 6 -c 1 -f -o gpurun_out/prof_pair_s1k11_$TAG $CMD > gpurun_out/ncu_f1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:rb_tc -s 0 -c 1 -f -o gpurun_out/prof_rb_s2k3_$TAG $CMD > gpurun_out/ncu_f2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:pair_tc -s 3 -c 1 -f -o gpurun_out/prof_pair_s1k11_$TAG $CMD > gpurun_out/ncu_f1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:rb_tc -s 1 -c 1 -f -o gpurun_out/prof_rb_s2k3_$TAG $CMD > gpurun_out/ncu_f2.log 2>&1
 python scripts/time_mel.py 1024 220500 3 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:mel_kernel -s 3 -c 1 -f -o gpurun_out/prof_mel_$TAG python scripts/time_mel.py 1024 220500 3 > gpurun_out/ncu_f3.log 2>&1
 ls -la gpurun_out/*_$TAG.* | head -20
