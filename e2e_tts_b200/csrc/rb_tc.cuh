@@ -112,7 +112,7 @@ rb_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ 
     tma_prefetch_desc(&tm_in);
     for (int i = 0; i < 8; ++i) mbar_init(&in_full[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&in_empty[i], 1);
+      mbar_init(&in_empty[i], 1 + kEpiWarps);   // the last c1's MMAs have read slab P + every epilogue warp has seeded x from it
       mbar_init(&acc_full[i], 1);
       mbar_init(&epi_done[i], kEpiWarps);
     }
@@ -390,7 +390,13 @@ rb_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ 
             tmem_ld_wait();
             if (j == 0) seed(p_addr + lane_off + offB, x_t + mB * p.nt + ccB * 16);
             act_store(vB, bv, inB, dst + offB);
-            if (j == 0) tmem_st_wait();
+            if (j == 0) {
+              tmem_st_wait();
+              __syncwarp();
+              // this warp's reads of slab P (the seed) are done: with one pair in the chain the MMAs of job 0 are the
+              // last readers the producer would otherwise wait for, and the next unit's TMA load could overtake the seed
+              if (lane == 0) mbar_arrive(&in_empty[ln]);
+            }
             fence_proxy_async_smem();   // the slab is read by the tensor core through the async proxy
           } else {
             epi_finish16(vA, bv, zq, sqa, eo, goffA, va);

@@ -10,6 +10,7 @@
 #include "../../include/e2e_tts_b200.h"
 #include "pair_host.cuh"
 #include "rb_host.cuh"
+#include "pair_tz_host.cuh"
 #include "small_kernels.cuh"
 
 using namespace e2e;
@@ -28,6 +29,7 @@ struct Layer {
   std::vector<ConvShape> alt_shape;
   std::vector<uint8_t*> alt_w;
   uint8_t* d_w = nullptr;    // packed 16-bit weights (or fp32 [k][cin] for L_POST)
+  uint8_t* d_wtz = nullptr;  // 32 -> 32 channel, dilation-1 convolutions: sliding-window array for pair_tz.cuh
   float* d_bias = nullptr;   // [n_total]
   std::vector<float> h_bias;  // host copy (the fused pair kernel takes its biases as kernel parameters)
   float post_bias = 0.f;
@@ -35,11 +37,13 @@ struct Layer {
 };
 
 struct Op {
-  int kind;   // 0 = mel_to_act, 1 = conv_tc, 2 = post, 3 = fused residual pair, 4 = fused whole ResBlock1
+  int kind;   // 0 = mel_to_act, 1 = conv_tc, 2 = post, 3 = fused residual pair, 4 = fused whole ResBlock1,
+              // 7 = fused residual pair of the C = 32 stage, four time steps per GEMM row (pair_tz.cuh)
   int layer;  // index into layers
   ConvPlan plan;
   PairPlan pair;
   RbPlan rb;
+  TzPlan tz;
 };
 
 struct PlanKey {
@@ -249,6 +253,8 @@ extern "C" int e2e_voc_create(const e2e_voc_config* cfg, e2e_voc** out) {
   if (rc_init) return rc_init;
   rc_init = rb_kernels_init();
   if (rc_init) return rc_init;
+  rc_init = tz_kernels_init();
+  if (rc_init) return rc_init;
   *out = v.release();
   return 0;
 }
@@ -257,6 +263,7 @@ extern "C" void e2e_voc_destroy(e2e_voc* v) {
   if (!v) return;
   for (auto& L : v->layers) {
     if (L.d_w) cudaFree(L.d_w);
+    if (L.d_wtz) cudaFree(L.d_wtz);
     if (L.d_bias) cudaFree(L.d_bias);
     for (uint8_t* w : L.alt_w)
       if (w) cudaFree(w);
@@ -365,6 +372,14 @@ extern "C" int e2e_voc_load_layer(e2e_voc* v, const char* name, const float* wei
     pack_conv_weights(L.alt_shape[a], wg.data(), pk.data(), v->f16);
     if (!L.alt_w[a] && (e = cudaMalloc(&L.alt_w[a], pk.size())) != cudaSuccess) return fail((int)e, "cudaMalloc");
     if ((e = cudaMemcpy(L.alt_w[a], pk.data(), pk.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return fail((int)e, "cudaMemcpy");
+  }
+  if (L.kind == L_CONV && L.cin == kTzC && L.cout == kTzC && s.cin == kTzC && s.n_total == kTzC && L.dil == 1 && L.k >= 3) {
+    // the same weights as a sliding-window array (pair_tz.cuh): c2 of every C = 32 pair, and c1 where it is undilated
+    std::vector<uint8_t> win(tz_window_bytes(L.k));
+    pack_tz_window(wg.data(), L.k, win.data(), v->f16);
+    if (!L.d_wtz && (e = cudaMalloc(&L.d_wtz, win.size())) != cudaSuccess) return fail((int)e, "cudaMalloc");
+    if ((e = cudaMemcpy(L.d_wtz, win.data(), win.size(), cudaMemcpyHostToDevice)) != cudaSuccess)
       return fail((int)e, "cudaMemcpy");
   }
   L.h_bias = bg;
@@ -534,6 +549,44 @@ static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B,
   return 0;
 }
 
+// The same pair on the C = 32 stage with four time steps per GEMM row (pair_tz.cuh).
+static bool tz_usable(const e2e_voc* v, int l1, int l2, int T) {
+  const Layer& L1 = v->layers[l1];
+  const Layer& L2 = v->layers[l2];
+  if (L1.cin != kTzC || L1.k != L2.k || L2.dil != 1 || !L2.d_wtz || (L1.dil == 1 && !L1.d_wtz)) return false;
+  return tz_supported(L1.cin, L1.k, L1.dil, T);
+}
+
+static int make_tz_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B, int T, const __nv_bfloat16* in,
+                      const __nv_bfloat16* sum_a, __nv_bfloat16* out_act, float slope, float divisor, int tiled) {
+  const Layer& L1 = v->layers[l1];
+  const Layer& L2 = v->layers[l2];
+  Op op;
+  op.kind = 7;
+  op.layer = l1;
+  int rc = plan_tz(op.tz, L1.k, L1.dil, B, T, v->n_sms);
+  if (rc) return rc;
+  TzParams& p = op.tz.p;
+  rc = tz_input_map(op.tz, in);
+  if (rc) return rc;
+  p.w1 = L1.dil == 1 ? L1.d_wtz : L1.d_w;
+  p.w2 = L2.d_wtz;
+  if (L1.h_bias.size() != (size_t)kTzC || L2.h_bias.size() != (size_t)kTzC) return fail(-2, "pair_tz: 32 channels only");
+  std::copy(L1.h_bias.begin(), L1.h_bias.end(), p.bias1);
+  std::copy(L2.h_bias.begin(), L2.h_bias.end(), p.bias2);
+  p.res_inv_slope = 10.0f;
+  p.sum_a = sum_a;
+  p.sum_tiled = sum_a != nullptr && (tiled & kSumTiled);
+  p.out_tiled = (tiled & kOutTiled) != 0;
+  p.out_act = out_act;
+  p.slope_mid = 0.1f;
+  p.slope = slope;
+  p.divisor = divisor;
+  p.f16 = v->f16;
+  ops.push_back(op);
+  return 0;
+}
+
 // One fused launch for a whole ResBlock1 (rb_tc.cuh): `in` holds bf16 leaky_relu(x, 0.1); l1[i] / l2[i] = layers of pair i.
 static int make_rb_op(e2e_voc* v, std::vector<Op>& ops, const int* l1, const int* l2, int n_pairs, int B, int T,
                       const __nv_bfloat16* in, const __nv_bfloat16* sum_a, __nv_bfloat16* out_act, float slope,
@@ -659,9 +712,12 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
           }
         }
         if (fused) {
-          rc = make_pair_op(v, ops, v->by_name[base + ".convs1." + std::to_string(m)],
-                            v->by_name[base + ".convs2." + std::to_string(m)], B, Ts, ain, sum_in, of32, oact, slope,
-                            divisor, tiled);
+          const int l1 = v->by_name[base + ".convs1." + std::to_string(m)];
+          const int l2 = v->by_name[base + ".convs2." + std::to_string(m)];
+          if (!of32 && tz_usable(v, l1, l2, Ts))
+            rc = make_tz_op(v, ops, l1, l2, B, Ts, ain, sum_in, oact, slope, divisor, tiled);
+          else
+            rc = make_pair_op(v, ops, l1, l2, B, Ts, ain, sum_in, of32, oact, slope, divisor, tiled);
           if (rc) return rc;
           ain = oact;
         } else if (c.resblock == 1) {
@@ -757,7 +813,7 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
   const std::vector<Op>& ops = it->second;
   size_t first_conv = ops.size(), last_conv = 0;
   for (size_t i = 0; i < ops.size(); ++i)
-    if (ops[i].kind == 1 || ops[i].kind == 3 || ops[i].kind == 4) {
+    if (ops[i].kind == 1 || ops[i].kind == 3 || ops[i].kind == 4 || ops[i].kind == 7) {
       first_conv = i < first_conv ? i : first_conv;
       last_conv = i;
     }
@@ -827,6 +883,9 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
       if (rc) return rc;
     } else if (op.kind == 4) {
       int rc = launch_rb(op.rb, st);
+      if (rc) return rc;
+    } else if (op.kind == 7) {
+      int rc = launch_tz(op.tz, st);
       if (rc) return rc;
     } else if (op.kind == 5) {
       const int Ts = T * v->hop, C = v->layers[v->by_name["conv_post"]].cin;
@@ -1118,6 +1177,7 @@ extern "C" void e2e_resblock_destroy(e2e_resblock* rb) {
   if (!rb) return;
   for (auto& L : rb->core.layers) {
     if (L.d_w) cudaFree(L.d_w);
+    if (L.d_wtz) cudaFree(L.d_wtz);
     if (L.d_bias) cudaFree(L.d_bias);
     for (uint8_t* w : L.alt_w)
       if (w) cudaFree(w);

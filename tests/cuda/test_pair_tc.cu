@@ -48,6 +48,11 @@ static const Cfg kCfgs[] = {
     {"perf c64 k11 d5", 64, 11, 5, 16, 55168, 0, 0, 0, 1},
     {"perf c32 k3 d1", 32, 3, 1, 16, 110336, 0, 0, 0, 1},
     {"perf c32 k11 d5", 32, 11, 5, 16, 110336, 0, 0, 0, 1},
+    {"perf c32 k7 d1", 32, 7, 1, 16, 110336, 0, 0, 0, 1},
+    {"perf c32 k7 d3", 32, 7, 3, 16, 110336, 0, 0, 0, 1},
+    {"perf c32 k7 d5", 32, 7, 5, 16, 110336, 0, 0, 0, 1},
+    {"perf c32 k11 d1", 32, 11, 1, 16, 110336, 0, 0, 0, 1},
+    {"perf c32 k11 d3", 32, 11, 3, 16, 110336, 0, 0, 0, 1},
 };
 static const int kNumCfgs = sizeof(kCfgs) / sizeof(kCfgs[0]);
 

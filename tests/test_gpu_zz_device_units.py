@@ -14,6 +14,7 @@ CONV_DIRECT = [0, 1, 2, 3, 4, 5, 6, 10, 11, 12, 13, 14]          # test_conv_tc.
 CONV_STAGED = [0, 1, 2, 3, 4, 5, 6, 7, 10, 11, 12, 13, 14, 25]   # ... and the staged TMA-store epilogue
 PAIR_SMALL = list(range(9))                                       # test_pair_tc.cu: every non-perf configuration
 RB_SMALL = list(range(9))                                         # test_rb_tc.cu: every non-perf configuration
+TZ_SMALL = list(range(12))                                        # test_pair_tz.cu: every non-perf configuration
 
 
 def _run(binary, cfg, env_extra):
@@ -47,3 +48,12 @@ def test_rb_tc_kernel_against_naive_cuda(cfg):
     """Fused whole ResBlock1 (three pairs chained, residual stream in TMEM) for C = 32 / 64 / 128, k = 3 / 5 / 7,
     one to three pairs, ragged tails, running-sum / divide epilogues."""
     _run("test_rb_tc_wd", cfg, {})
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg", TZ_SMALL)
+def test_pair_tz_kernel_against_naive_cuda(cfg):
+    """Fused pair of the C = 32 stage with four time steps per GEMM row (sliding-window weights, N = 128 MMAs; dilated c1
+    as N = 32 MMAs): k = 3 / 5 / 7 / 11, d = 1 / 2 / 3 / 5, ragged tails, running sums in the natural and the tiled8
+    layout, odd unit counts per CTA."""
+    _run("test_pair_tz_wd", cfg, {})
