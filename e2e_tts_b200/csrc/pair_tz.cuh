@@ -69,22 +69,25 @@ struct TzParams {
   __nv_bfloat16* out_act;        // leaky_relu(result, slope)
 };
 
-// packed fp32 pairs (FADD2 / FMUL2 on sm_100): the epilogues are issue-bound (profiles/r02_ncu_full_rb_s2k3_e.txt: 66 %)
-__device__ __forceinline__ unsigned long long tz_pk2(float lo, float hi) {
-  unsigned long long r;
+// packed fp32 pairs (FADD2 / FMUL2 on sm_100) for the adds and multiplies of the two epilogues; bit-identical to the scalar
+// forms.  (The same change in the shared epilogues of conv_tc / pair_tc / rb_tc was measured over the whole forward and
+// is not kept: profiles/r02_experiments_notes.md §10.)
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_pack(float lo, float hi) {
+  f32x2 r;
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
 }
-__device__ __forceinline__ void tz_up2(unsigned long long v, float& lo, float& hi) {
+__device__ __forceinline__ void f2_unpack(f32x2 v, float& lo, float& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
-__device__ __forceinline__ unsigned long long tz_add2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
+__device__ __forceinline__ f32x2 f2_add(f32x2 a, f32x2 b) {
+  f32x2 r;
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-__device__ __forceinline__ unsigned long long tz_mul2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
+__device__ __forceinline__ f32x2 f2_mul(f32x2 a, f32x2 b) {
+  f32x2 r;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
@@ -312,15 +315,15 @@ pair_tz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       constexpr bool F16 = decltype(f16tag)::value;
       if (inside) {
         uint32_t pk[8];
-        const unsigned long long s2 = tz_pk2(smid, smid);
+        const f32x2 s2 = f2_pack(smid, smid);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const unsigned long long f = tz_add2(tz_pk2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
-                                               tz_pk2(p.bias1[c0 + 2 * i], p.bias1[c0 + 2 * i + 1]));
-          const unsigned long long g = tz_mul2(f, s2);
+          const f32x2 f = f2_add(f2_pack(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
+                                               f2_pack(p.bias1[c0 + 2 * i], p.bias1[c0 + 2 * i + 1]));
+          const f32x2 g = f2_mul(f, s2);
           float f0, f1, g0, g1;
-          tz_up2(f, f0, f1);
-          tz_up2(g, g0, g1);
+          f2_unpack(f, f0, f1);
+          f2_unpack(g, g0, g1);
           pk[i] = pack16t<F16>(fmaxf(f0, g0), fmaxf(f1, g1));
         }
         st_shared_u4(dst, make_uint4(pk[0], pk[1], pk[2], pk[3]));
@@ -355,18 +358,18 @@ pair_tz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       uint32_t pk[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        unsigned long long f = tz_add2(tz_pk2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
-                                       tz_pk2(p.bias2[c0 + 2 * i], p.bias2[c0 + 2 * i + 1]));
+        f32x2 f = f2_add(f2_pack(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])),
+                                       f2_pack(p.bias2[c0 + 2 * i], p.bias2[c0 + 2 * i + 1]));
         if (has_sum) {
           float lo, hi;
           unpack16t<F16>(sw[i], lo, hi);
-          f = tz_add2(f, tz_pk2(lo, hi));
+          f = f2_add(f, f2_pack(lo, hi));
         }
-        if (use_scale) f = tz_mul2(f, tz_pk2(scale, scale));
-        const unsigned long long g = tz_mul2(f, tz_pk2(slope, slope));
+        if (use_scale) f = f2_mul(f, f2_pack(scale, scale));
+        const f32x2 g = f2_mul(f, f2_pack(slope, slope));
         float f0, f1, g0, g1;
-        tz_up2(f, f0, f1);
-        tz_up2(g, g0, g1);
+        f2_unpack(f, f0, f1);
+        f2_unpack(g, g0, g1);
         pk[i] = pack16t<F16>(fmaxf(f0, g0), fmaxf(f1, g1));   // leaky_relu, 0 < slope <= 1
       }
       st_global_256(p.out_act + off, make_uint4(pk[0], pk[1], pk[2], pk[3]), make_uint4(pk[4], pk[5], pk[6], pk[7]));

@@ -668,7 +668,10 @@ static int build_plan(e2e_voc* v, int B, int T, void* ws, std::vector<Op>& ops) 
       bool fused = c.resblock == 1 && std::getenv("E2E_NO_PAIR_FUSION") == nullptr;
       for (int m = 0; m < nd && fused; ++m) fused = pair_supported(chs, ks, c.resblock_dilation_sizes[j][m]);
       // Whole-resblock fusion (rb_tc.cuh: residual stream in TMEM, one launch per ResBlock1) where its halo is cheap
-      if (fused && nd <= kRbMaxPairs && rb_supported(chs, ks, c.resblock_dilation_sizes[j], nd)) {
+      // (E2E_TZ_K3=1: experiment - the k = 3 resblock of the C = 32 stage as three pair_tz launches instead of the chain)
+      static const char* etz3 = std::getenv("E2E_TZ_K3");
+      const bool tz_instead = etz3 && etz3[0] == '1' && chs == kTzC && tz_supported(chs, ks, 1, Ts);
+      if (fused && !tz_instead && nd <= kRbMaxPairs && rb_supported(chs, ks, c.resblock_dilation_sizes[j], nd)) {
         int l1[kRbMaxPairs], l2[kRbMaxPairs];
         for (int m = 0; m < nd; ++m) {
           l1[m] = v->by_name[base + ".convs1." + std::to_string(m)];
