@@ -30,7 +30,7 @@ for k, i in enumerate(fw):
     out.append("%3d %-30s grid=%-14s %8.1f us  dram rd %7.1f MB  wr %7.1f MB" % (k, n, d["grid"], t, rb / 1e6, wb / 1e6))
     tot_t += t
     tot_b += rb + wb
-    if "tc_kernel" in n:   # conv_tc / pair_tc / rb_tc
+    if "tc_kernel" in n or "tz_kernel" in n:   # conv_tc / pair_tc / rb_tc / pair_tz
         tc_b += rb + wb
         tc_t += t
 hdr = ("forward #1 of `python bench.py --steps 1 --warmup 3 --passes 1 --quick --no-side` under ncu (serialised, cold-cache, no "
@@ -42,7 +42,7 @@ json.dump({"dram_bytes_per_step_tcgen05": tc_b, "dram_bytes_per_step_all": tot_b
            "source": "profiles/%s (ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, one forward)" % name},
           open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
 print(hdr)
-for src, dst in (("pair_s1k11", "pair_s1k11"), ("rb_s2k3", "rb_s2k3"), ("mel", "mel")):
+for src, dst in (("pair_s1k11", "pair_s1k11"), ("rb_s2k3", "rb_s2k3"), ("tz_s3k11", "tz_s3k11"), ("mel", "mel")):
     rep = os.path.join(G, "prof_%s_%s.ncu-rep" % (src, tag))
     if os.path.exists(rep):
         txt = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep, "14"],
