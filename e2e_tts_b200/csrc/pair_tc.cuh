@@ -485,11 +485,11 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
       const int t8 = (p.T + 7) >> 3, c16 = p.nt >> 4;
       const size_t ta = (p.sum_tiled | p.out_tiled) && va ? tiled8_off(b, t0 + oa, ccA, t8, c16) : 0;
       const size_t tb = (p.sum_tiled | p.out_tiled) && vb ? tiled8_off(b, t0 + ob, ccB, t8, c16) : 0;
-      if (va) {
+      if (va && p.res_act) {   // (res_act == nullptr: timing experiments of tests/cuda only - the residual is always present)
         ld_global_256(p.res_act + offa, rqa[0], rqa[1]);
         if (p.sum_a) ld_global_256(p.sum_a + (p.sum_tiled ? ta : offa), sqa[0], sqa[1]);
       }
-      if (vb) {
+      if (vb && p.res_act) {
         ld_global_256(p.res_act + offb, rqb[0], rqb[1]);
         if (p.sum_a) ld_global_256(p.sum_a + (p.sum_tiled ? tb : offb), sqb[0], sqb[1]);
       }

@@ -255,6 +255,10 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
+  if (argc > 3 && atoi(argv[3]) == 1) {   // experiment: what the residual's global loads cost (timing only)
+    p.res_act = nullptr;
+    printf("  dbg: no residual loads\n");
+  }
   for (int i = 0; i < 2; ++i) launch_pair(plan, 0);
   CK(cudaEventRecord(e0));
   for (int i = 0; i < reps; ++i) launch_pair(plan, 0);
