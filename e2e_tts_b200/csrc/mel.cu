@@ -141,6 +141,11 @@ __device__ __forceinline__ void group_sync(int g) {
 __device__ __forceinline__ int k1_of(int h) { return (0x56327410 >> (4 * h)) & 7; }   // {0,1,4,7,2,3,6,5}
 __device__ __forceinline__ int h_of(int k1) { return (0x36725410 >> (4 * k1)) & 7; }  // inverse: k1 0..7 -> h
 
+// DMAX = registers d of the last pass that hold bins the filterbank reads (bin k = k1 + 8 c + 64 d): 6 when the bank ends
+// below bin 384 (the e2e-tts bank: fmax = 8 kHz -> bin 371), else 8.  A compile-time bound: a run-time `continue` costs
+// more than it saves (it splits the recombination into branchy blocks and the shuffles no longer overlap; measured
+// 1.68 -> 1.73 ms with the run-time bound, 1.68 -> 1.58 ms with this one, profiles/r02_experiments_notes.md §14).
+template <int DMAX>
 __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   float* audio = reinterpret_cast<float*>(smem);                    // [kAudio]
@@ -261,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
     float* mrow = mag_all + fl * p.magp;
 #pragma unroll
     for (int dd = 0; dd < 8; ++dd) {
+      if (7 - dd >= DMAX) continue;   // compile-time: nobody reads these bins (nor needs the partner values for them)
       float ax, ay;
       up2(a[dd], ax, ay);
       float bx = __shfl_sync(0xffffffffu, ax, lane_p);
@@ -405,7 +411,9 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
   up((void**)&m->d_fbw, wpk.data(), wpk.size() * 4);
   up((void**)&m->d_meta, meta.data(), meta.size() * 4);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
+    e = cudaFuncSetAttribute(mel_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(mel_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes);
   if (e != cudaSuccess) {
     e2e_mel_destroy(m);
     return fail((int)e, std::string("e2e_mel_create: ") + cudaGetErrorString(e));
@@ -455,7 +463,10 @@ extern "C" int e2e_mel_forward(e2e_mel* m, const float* wav, int32_t B, int64_t 
   p.fb_w = m->d_fbw;
   p.fb_meta = m->d_meta;
   dim3 grid((unsigned)((T + kF - 1) / kF), (unsigned)B);
-  mel_kernel<<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  if (m->nb <= 6 * 64)
+    mel_kernel<6><<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  else
+    mel_kernel<8><<<grid, kThreads, m->smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail((int)e, std::string("mel_kernel launch: ") + cudaGetErrorString(e));
   return 0;

@@ -1,6 +1,7 @@
 // HiFi-GAN generator on B200: layer table, weight packing, launch plans and the forward pass.
 // Mirrors the structure of the reference generator (e2e_tts/models/vocoder/generator.py:13-53 and
 // layers.py:10-69) as a list of tcgen05 convolution launches plus two small CUDA-core kernels.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -808,6 +809,16 @@ static int voc_forward_impl(e2e_voc* v, const float* mel, int64_t sB, int64_t sC
     std::vector<Op> ops;
     int rc = build_plan(v, B, T, workspace, ops);
     if (rc) return rc;
+    if (std::getenv("E2E_DUMP_PLAN"))   // debugging aid: one line per launch of the new plan
+      for (size_t i = 0; i < ops.size(); ++i) {
+        const Op& o = ops[i];
+        if (o.kind == 1)
+          fprintf(stderr, "plan[%zu] conv_tc %-28s mt=%d cg=%d staged=%d nt=%d taps=%d grid=%u smem=%d units=%d\n", i,
+                  v->layers[o.layer].name.c_str(), o.plan.p.mt, o.plan.cg, o.plan.staged, o.plan.p.nt, o.plan.p.taps,
+                  o.plan.grid.x, o.plan.smem_bytes, o.plan.p.n_units);
+        else
+          fprintf(stderr, "plan[%zu] kind=%d %s\n", i, o.kind, v->layers[o.layer].name.c_str());
+      }
     if (v->plans.size() > 64) drop_plans(v);
     it = v->plans.emplace(key, std::move(ops)).first;
   }
