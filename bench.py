@@ -88,9 +88,9 @@ def ncu_traffic():
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
             t = json.load(f)
-        return float(t["dram_bytes_per_step_tcgen05"]), str(t.get("source", ""))
+        return float(t["dram_bytes_per_step_tcgen05"]), str(t.get("source", "")), t.get("tensor_pipe_active_pct_tcgen05")
     except Exception:
-        return None, ""
+        return None, "", None
 
 
 class ClockSampler(threading.Thread):
@@ -648,7 +648,7 @@ def main():
     e2e_value = audio_s_pass * n_pass / (e2e_ms * 1e-3)
     del pipe
 
-    traffic, traffic_src = ncu_traffic()
+    traffic, traffic_src, tensor_pipe_pct = ncu_traffic()
     conv_tflops = B * T * CONV_TC_FLOP_PER_FRAME / (conv_ms * 1e-3) * 1e-12
     launches = voc.launches_per_forward()
     config = workload_config(world)
@@ -671,6 +671,9 @@ def main():
                      "peak_source": peaks["source"] + ": bf16_tflops_sustained (the kernels are timed inside a >= 2 s region); "
                                     "frac_burst uses bf16_tflops",
                      "traffic_note": ("DRAM bytes per cfg2 pass over the same launches, " + traffic_src) if traffic else "",
+                     # BASELINE metric, second half ("vocoder tensor-pipe util %"): ncu sm__pipe_tensor_cycles_active of the
+                     # same launches, weighted by launch time, from the committed launch list (not measured in this run)
+                     "tensor_pipe_active_pct_ncu": tensor_pipe_pct if (world == 1) else None,
                      "note": "%d tensor-core launches per pass, %.3f ms of the %.3f ms pass (CUDA events around them, "
                              "mean over %d passes, rank %d)" % (launches - 2, conv_ms, ms_step / R, n_pass, rank)},
     }

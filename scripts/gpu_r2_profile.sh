@@ -2,7 +2,8 @@
 # Runs on the GPU box: the evidence committed under profiles/ for round 2 (scripts/collect_profiles_r2.py <tag> turns
 # gpurun_out/ into profiles/r02_*):
 #   1. pytest -m gpu (with the parity-margin log), the default bench line (all workloads + baselines), the reference arm
-#   2. ncu launch list of one short bench run with per-launch DRAM bytes (time + traffic per launch)
+#   2. ncu launch list of one short bench run with per-launch DRAM bytes and tensor-pipe activity (time + traffic + the
+#      BASELINE metric's "vocoder tensor-pipe util %" per launch)
 #   3. ncu --set full of the dominant kernel (stage-1 k = 11 pair), the fused whole-resblock kernel, the stage-3 pair_tz
 #      kernel (k = 11, d = 1) and the mel kernel
 cd "$(dirname "$0")/.."
@@ -16,7 +17,7 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 E2E_OPERAND_DTYPE=fp16 timeout 600 python bench.py --quick --no-side > gpurun_out/bench_fp16_$TAG.json 2>/dev/null; cut -c1-200 gpurun_out/bench_fp16_$TAG.json
 CMD="python bench.py --steps 1 --warmup 3 --passes 1 --quick --no-side"
 $CMD > gpurun_out/ncu_plain_$TAG.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 520 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_l.log 2>&1
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__cycles_elapsed.avg.per_second --clock-control none -c 520 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_l.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pair_tc -s 3 -c 1 -f -o gpurun_out/prof_pair_s1k11_$TAG $CMD > gpurun_out/ncu_f1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rb_tc -s 1 -c 1 -f -o gpurun_out/prof_rb_s2k3_$TAG $CMD > gpurun_out/ncu_f2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:pair_tz -s 3 -c 1 -f -o gpurun_out/prof_tz_s3k11_$TAG $CMD > gpurun_out/ncu_f4.log 2>&1
