@@ -66,6 +66,34 @@ __device__ __forceinline__ size_t tiled8_off(int b, int t, int chunk16, int t8, 
   return ((static_cast<size_t>(b) * t8 + (t >> 3)) * c16 + chunk16) * 128 + (t & 7) * 16;
 }
 
+// The running sum a unit's last epilogue will add is read once, two or three launches after it was written: by then it
+// has left L2, and the epilogue's loads (issued one job ahead) still see most of the DRAM latency - the third pair of
+// every resblock ran 10-36 us longer than its siblings (profiles/r02_launches_g_time_dram.txt).  The slab producer
+// therefore asks for the unit's rows [t0, t1) of utterance b - one contiguous range in either layout - to be brought
+// into L2 when it loads the unit's input slab, two units ahead of that epilogue.  C = channels, T = rows per utterance.
+__device__ __forceinline__ void prefetch_sum_rows(const __nv_bfloat16* sum, int tiled, int b, int t0, int t1, int T, int C) {
+  if (t1 > T) t1 = T;
+  if (t0 < 0) t0 = 0;
+  if (t1 <= t0) return;
+  size_t first, last;   // elements
+  if (tiled) {
+    const int t8 = (T + 7) >> 3;
+    first = (static_cast<size_t>(b) * t8 + (t0 >> 3)) * C * 8;
+    last = (static_cast<size_t>(b) * t8 + ((t1 + 7) >> 3)) * C * 8;
+  } else {
+    first = (static_cast<size_t>(b) * T + t0) * C;
+    last = (static_cast<size_t>(b) * T + t1) * C;
+  }
+  const char* base = reinterpret_cast<const char*>(sum + first);
+  size_t bytes = (last - first) * 2;
+  while (bytes) {   // (C * 2 is a multiple of 64 bytes: every piece stays 16-byte aligned)
+    const uint32_t n = bytes > 65536 ? 65536u : static_cast<uint32_t>(bytes);
+    bulk_prefetch_l2(base, n);
+    base += n;
+    bytes -= n;
+  }
+}
+
 struct EpiOut {
   const __nv_bfloat16* sum_a;  // bf16 running resblock sum to add (nullptr = absent)
   float* out_f32;

@@ -55,6 +55,7 @@ struct PairParams {
   const __nv_bfloat16* res_act;  // == the kernel's input tensor (bf16 leaky_relu(x)), read for the residual
   const __nv_bfloat16* sum_a;    // bf16 running sum over the stage's resblocks (generator.py:44-47) or nullptr
   int sum_tiled;                 // sum_a is in the tiled8 layout (epilogue.cuh)
+  int no_sum_prefetch;           // experiments (E2E_NO_SUM_PREFETCH=1): no L2 prefetch of the running sum by the producer
   int out_tiled;                 // out_act is written in the tiled8 layout (direct stores; never with STAGED)
   int f16;                       // 16-bit tensors and operands are fp16 instead of bf16 (ptx.cuh pack16)
   __nv_bfloat16* out_act;        // bf16 leaky_relu(result, slope), written through tm_out / tm_out2 (TMA stores)
@@ -184,6 +185,8 @@ pair_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
                           &a_full[ln * 4 + pn]);
           }
         }
+        if (p.sum_a && !p.no_sum_prefetch && b < p.B)   // see prefetch_sum_rows (epilogue.cuh)
+          prefetch_sum_rows(p.sum_a, p.sum_tiled, b, t0, t0 + p.r_out, p.T, p.nt);
       }
     }
   } else if (warp == 1) {

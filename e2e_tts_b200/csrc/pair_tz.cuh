@@ -64,6 +64,7 @@ struct TzParams {
   alignas(16) float bias2[kTzC];   // c2's bias: x lives in TMEM without it
   const __nv_bfloat16* sum_a;    // running sum over the stage's resblocks (generator.py:44-47) or nullptr
   int sum_tiled, out_tiled;      // tiled8 layouts of the [T][32] view (epilogue.cuh)
+  int no_sum_prefetch;           // experiments (E2E_NO_SUM_PREFETCH=1): no L2 prefetch of the running sum by the producer
   int f16;                       // 16-bit tensors and operands are fp16 instead of bf16
   int dbg;                       // experiments only (tests/cuda): 1 = no seed, 2 = no intermediate slab stores
   __nv_bfloat16* out_act;        // leaky_relu(result, slope)
@@ -166,6 +167,10 @@ pair_tz_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant_
         uint8_t* dst = slab_p + ln * slab_bytes;
         tma_load_3d(dst, &tm_in, 0, ts, uit.b, &in_full[ln]);
         tma_load_3d(dst + panel_bytes, &tm_in, 64, ts, uit.b, &in_full[ln]);
+        if (p.sum_a && !p.no_sum_prefetch) {   // rows of the [T][32] view this unit stores; see prefetch_sum_rows (epilogue.cuh)
+          const int t0 = kTzG * uit.tile * p.r_out;
+          prefetch_sum_rows(p.sum_a, p.sum_tiled, uit.b, t0, t0 + kTzG * p.r_out, p.T, kTzC);
+        }
       }
     }
   } else if (warp == 1) {

@@ -216,6 +216,11 @@ __device__ __forceinline__ void tc_fence_after_sync() {
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
 }
+// Bulk prefetch of a contiguous global range into L2 (no shared-memory destination, no completion to wait for):
+// `bytes` a multiple of 16, `gptr` 16-byte aligned.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
 // 3-D tiled load: coordinates are (c0 = innermost element index, c1, c2); out-of-bounds elements
 // (including negative coordinates) are zero-filled, which is exactly Conv1d's per-layer zero padding.
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,

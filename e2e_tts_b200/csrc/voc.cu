@@ -539,6 +539,7 @@ static int make_pair_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B,
   p.out_act = out_act;
   p.sum_tiled = sum_a != nullptr && (tiled & kSumTiled);
   p.out_tiled = (tiled & kOutTiled) != 0;
+  p.no_sum_prefetch = std::getenv("E2E_NO_SUM_PREFETCH") != nullptr;
   if (p.out_tiled) op.pair.staged = false;   // the TMA store writes the natural layout
   rc = pair_output_maps(op.pair, out_act, B, T, L1.cin);
   if (rc) return rc;
@@ -579,6 +580,7 @@ static int make_tz_op(e2e_voc* v, std::vector<Op>& ops, int l1, int l2, int B, i
   p.sum_a = sum_a;
   p.sum_tiled = sum_a != nullptr && (tiled & kSumTiled);
   p.out_tiled = (tiled & kOutTiled) != 0;
+  p.no_sum_prefetch = std::getenv("E2E_NO_SUM_PREFETCH") != nullptr;
   p.out_act = out_act;
   p.slope_mid = 0.1f;
   p.slope = slope;

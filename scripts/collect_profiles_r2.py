@@ -31,7 +31,8 @@ for k, i in enumerate(fw):
     n = d["name"].split("(")[0].split("::")[-1][:30]
     line = "%3d %-30s grid=%-14s %8.1f us  dram rd %7.1f MB  wr %7.1f MB" % (k, n, d["grid"], t, rb / 1e6, wb / 1e6)
     if have_tp:
-        line += "  tensor pipe %5.1f %% @ %.2f GHz" % (d[TP], d.get("sm__cycles_elapsed.avg.per_second", 0.0))
+        ghz = d.get("sm__cycles_elapsed.avg.per_second", 0.0)
+        line += "  tensor pipe %5.1f %% @ %.2f GHz" % (d[TP], ghz * 1e-9 if ghz > 1e6 else ghz)
         tp_all += d[TP] * t
     out.append(line)
     tot_t += t
