@@ -52,7 +52,8 @@ FLOP_PER_FRAME = 614105088          # 2*MACs of all 78 convs p
 CONV_TC_FLOP_PER_FRAME = FLOP_PER_FRAME - 114688   # everything but conv_post runs on the tensor cores
 MEL_L = 220500           # 10 s clip
 MEL_CLIPS = 1024
-MEL_WARP_INSTR_PER_FRAME = 1147   # ncu smsp__inst_executed.sum / 881 664 frames, profiles/r02_ncu_full_mel_e.txt
+MEL_DRAM_BYTES_NCU = 904063232 + 265385472   # dram__bytes_read.sum + dram__bytes_write.sum of one 1024-clip launch, same file
+MEL_WARP_INSTR_PER_FRAME = 1043   # ncu smsp__inst_executed.sum / 881 664 frames, profiles/r02_ncu_full_mel_h.txt
 METRIC = "audio_seconds_synthesized_per_second"
 UNIT = "audio-s/s"
 NUMERICS = ("bf16 operands / fp32 accumulate; activations stored once as bf16 leaky_relu(x); residual adds and the "
@@ -433,18 +434,20 @@ def side_workloads(voc, dev, peaks, quick: bool):
     Tm = mel.shape[-1]
     alg = clips * (4 * MEL_L + 4 * 81 * Tm)          # fp32 audio in, fp32 mel (80) + energy (1) out
     gbs = alg / (ms * 1e-3) * 1e-9
-    # What bounds the kernel is instruction issue, not HBM: 1 147 warp instructions per frame
-    # (ncu smsp__inst_executed.sum / frames, profiles/r02_ncu_full_mel_e.txt) at 4 issue slots per cycle and SM
+    # What bounds the kernel is instruction issue / latency, not HBM: 1 043 warp instructions per frame
+    # (ncu smsp__inst_executed.sum / frames, profiles/r02_ncu_full_mel_h.txt) at 4 issue slots per cycle and SM
     issue_floor_ms = clips * Tm * MEL_WARP_INSTR_PER_FRAME / (148 * 4 * 1.965e9) * 1e3
     w["cfg5_mel"] = {"workload": "%d clips x 10 s (L=220500 -> T=%d frames), TorchSTFT.mel_spectrogram(return_energy=True), "
                                  "range check off (no host sync)" % (clips, Tm),
                      "ms_per_pass": ms, "value": clips * MEL_L / SR / (ms * 1e-3), "unit": UNIT,
                      "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s",
-                                  "frac": gbs / peaks["hbm"], "traffic": None, "kernel": "mel_kernel",
+                                  "frac": gbs / peaks["hbm"], "traffic": MEL_DRAM_BYTES_NCU if clips == 1024 else None,
+                                  "kernel": "mel_kernel",
                                   "algorithmic_bytes": alg, "hbm_floor_ms": alg / (peaks["hbm"] * 1e9) * 1e3,
                                   "issue_slot_floor_ms": issue_floor_ms, "issue_slot_frac": issue_floor_ms / ms,
                                   "note": "SURVEY.md §8 d7 names HBM as this path's roofline and `frac` is reported against it; "
-                                          "the kernel is bound by instruction issue (1147 warp instructions per frame, ncu): "
+                                          "the kernel is bound by dependent-instruction latency at ~50 % issue-slot use (%d warp instructions "
+                                          "per frame, ncu): " % MEL_WARP_INSTR_PER_FRAME +
                                           "issue_slot_frac = time at 100 % issue-slot use / measured time",
                                   "peak_source": peaks["source"]}}
     del wav, mel, en
