@@ -4,7 +4,7 @@ import collections, os, re, subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "e2e_tts_b200", "lib", "libe2e_tts_b200.so")
-KEEP = ["UTCHMMA.2CTA", "UTCHMMA", "HMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "FADD2", "FMUL2",
+KEEP = ["UTCHMMA.2CTA", "UTCHMMA", "HMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKPF", "UTCBAR", "SYNCS", "FADD2", "FMUL2",
         "FFMA2", "MUFU"]
 
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
@@ -32,7 +32,7 @@ out = ["cuobjdump -sass e2e_tts_b200/lib/libe2e_tts_b200.so (built by e2e_tts_b2
        "-lineinfo -O3); regenerate with scripts/sass_opcode_counts.py",
        "opcode counts per kernel (SASS mnemonics: UTCHMMA = tcgen05.mma kind::f16, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG = TMA "
        "tensor load/store,",
-       "UBLKCP = cp.async.bulk, UTCBAR = tcgen05.commit, FADD2/FMUL2/FFMA2 = packed f32x2; HMMA (legacy mma.sync) must be 0)", ""]
+       "UBLKCP = cp.async.bulk, UBLKPF = cp.async.bulk.prefetch.L2, UTCBAR = tcgen05.commit, FADD2/FMUL2/FFMA2 = packed f32x2; HMMA (legacy mma.sync) must be 0)", ""]
 hmma = 0
 for n, d in zip(names, dem):
     d = d.replace("(anonymous namespace)::", "").replace("(bool)", "")
