@@ -35,3 +35,40 @@ def test_host_f16_bf16_conversions(tmp_path):
     assert np.array_equal(got[:, 0].astype(np.uint16), want16)
     wantbf = torch.from_numpy(vals).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
     assert np.array_equal(got[:, 1].astype(np.uint16), wantbf)
+
+
+def _tiled8_off(b, t, chunk16, t8, c16):
+    """epilogue.cuh tiled8_off: element offset of 16 channels of row t in [B][ceil(T/8)][C/16][8][16]."""
+    return ((b * t8 + (t >> 3)) * c16 + chunk16) * 128 + (t & 7) * 16
+
+
+def _prefetch_range(tiled, b, t0, t1, T, C):
+    """epilogue.cuh prefetch_sum_rows: the element range [first, last) the slab producer asks L2 to fetch."""
+    t1 = min(t1, T)
+    t0 = max(t0, 0)
+    if t1 <= t0:
+        return None
+    if tiled:
+        t8 = (T + 7) >> 3
+        return (b * t8 + (t0 >> 3)) * C * 8, (b * t8 + ((t1 + 7) >> 3)) * C * 8
+    return (b * T + t0) * C, (b * T + t1) * C
+
+
+@pytest.mark.parametrize("C,T,r_out", [(128, 27584, 118), (64, 55168, 246), (32, 110336, 4 * 126), (32, 96, 40)])
+def test_sum_prefetch_range_covers_exactly_the_rows_the_epilogue_reads(C, T, r_out):
+    """The rows a unit's last epilogue reads from the running-sum tensor form ONE contiguous range in the tiled8 layout
+    (and in the natural one): every 16-channel item of rows [t0, t1) lies inside the prefetched range, the range is
+    16-byte aligned and holds no whole 8-row group that the unit does not touch."""
+    t8, c16 = (T + 7) >> 3, C // 16
+    for b in (0, 3):
+        n_tiles = (T + r_out - 1) // r_out
+        for tile in sorted({0, 1, min(7, n_tiles - 1), n_tiles - 1}):
+            t0, t1 = tile * r_out, tile * r_out + r_out
+            first, last = _prefetch_range(1, b, t0, t1, T, C)
+            assert first % 8 == 0 and last % 8 == 0 and last > first     # 16-byte pieces of bf16
+            offs = [_tiled8_off(b, t, ch, t8, c16) for t in range(t0, min(t1, T)) for ch in range(c16)]
+            assert min(offs) >= first and max(offs) + 16 <= last
+            assert min(offs) - first < C * 8 and last - (max(offs) + 16) < C * 8   # tight to the 8-row group
+            nf, nl = _prefetch_range(0, b, t0, t1, T, C)
+            assert nf == (b * T + t0) * C and nl == (b * T + min(t1, T)) * C and nf % 8 == 0
+    assert _prefetch_range(1, 0, T, T + r_out, T, C) is None
