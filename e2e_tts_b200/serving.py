@@ -49,7 +49,8 @@ class HostPipeline:
         self._takes_out = _accepts_out(vocoder)
         self._ev_in = [torch.cuda.Event() for _ in range(self.depth)]
         self._ev_comp = [torch.cuda.Event() for _ in range(self.depth)]
-        self._ev_out: List[torch.cuda.Event] = []
+        self._ev_out: List[torch.cuda.Event] = []   # copy-out events of batches _base .. _n - 1
+        self._base = 0
         self._n = 0
 
     def submit(self, mel_host: torch.Tensor, wav_host: torch.Tensor) -> int:
@@ -96,11 +97,19 @@ class HostPipeline:
         self._ev_copied[slot] = ev_out
         self._ev_out.append(ev_out)
         self._n += 1
+        # a serving loop that never calls drain() must not accumulate one event per batch: forget the oldest events once
+        # they have completed (the copy-out stream is in order, so everything older has completed too)
+        while len(self._ev_out) > 4 * self.depth + 32 and self._ev_out[0].query():
+            self._ev_out.pop(0)
+            self._base += 1
         return i
 
     def wait(self, index: int) -> None:
         """Blocks the host until batch `index` is in its host buffer."""
-        self._ev_out[index].synchronize()
+        if index >= self._n:
+            raise IndexError("batch %d has not been submitted" % index)
+        if index >= self._base:                                # (older batches completed before their events were dropped)
+            self._ev_out[index - self._base].synchronize()
 
     def join(self) -> None:
         """Makes the caller's current stream wait for everything submitted so far (no host blocking)."""
@@ -113,4 +122,5 @@ class HostPipeline:
         if self._ev_out:
             self._ev_out[-1].synchronize()
         self._ev_out.clear()
+        self._base = 0
         self._n = 0

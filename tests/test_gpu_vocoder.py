@@ -302,6 +302,30 @@ def test_host_pipeline_variable_batch_shapes():
             assert torch.equal(o, w)
 
 
+def test_host_pipeline_long_loop_keeps_a_bounded_event_list():
+    """A serving loop never calls drain(): the pipeline forgets completed copy-out events (wait() on a forgotten batch
+    returns at once), so its bookkeeping stays bounded, and the results stay those of direct calls."""
+    voc, _ = build(ho.DEFAULT_CONFIG, 16, "strong")
+    mels = [mel_like(1, 12, 90 + i).pin_memory() for i in range(3)]
+    outs = [torch.empty(1, 12 * 256).pin_memory() for _ in range(4)]
+    with torch.no_grad():
+        want = [voc(m.cuda()).squeeze(1).cpu() for m in mels]
+    pipe = pkg.HostPipeline(voc)
+    n = 300
+    for i in range(n):
+        idx = pipe.submit(mels[i % 3], outs[i % 4])
+        if i % 4 == 3:
+            pipe.wait(idx - 2)      # the caller's contract: a host buffer is reused only after its batch has landed
+        assert idx == i
+    pipe.wait(n - 1)
+    pipe.wait(0)                    # long forgotten: returns immediately
+    assert len(pipe._ev_out) <= 4 * pipe.depth + 33
+    assert torch.equal(outs[(n - 1) % 4], want[(n - 1) % 3])
+    with pytest.raises(IndexError):
+        pipe.wait(n)
+    pipe.drain()
+
+
 ALT_CONFIGS = {
     # four x4 stages (hop 256), ResBlock1
     "x4x4x4x4": {"resblock": 1, "upsample_rates": [4, 4, 4, 4], "upsample_kernel_sizes": [8, 8, 8, 8],
