@@ -228,6 +228,7 @@ def test_fp16_operand_mode_full_utterance_and_pcm():
         pkg.HifiGan(ho.DEFAULT_CONFIG, operand_dtype="fp8")
 
 
+@pytest.mark.skipif(os.environ.get("E2E_NO_GRAPH") is not None, reason="E2E_NO_GRAPH switches CUDA-graph replay off")
 def test_cuda_graph_replay_is_bit_identical_and_tracks_weight_reloads():
     """A forward on buffers seen before is captured into a CUDA graph (2nd call) and replayed (3rd on): same bits as
     the eager launches, a changed input buffer content is picked up (the graph reads the buffer, not a snapshot),
