@@ -151,9 +151,8 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
   float* audio = reinterpret_cast<float*>(smem);                    // [kAudio]
   float2* sx = reinterpret_cast<float2*>(audio + kAudio);           // [kGroups][kSx]
   float* mag_all = reinterpret_cast<float*>(sx + kGroups * kSx);    // [kF][magp]
-  float* energy_s = mag_all + kF * p.magp;                          // [kF]
-  float* red_s = energy_s + kF;                                     // [kGroups][2]
-  float* fbw_s = red_s + kGroups * 2;                               // [n_w]
+  float* red_s = mag_all + kF * p.magp;                             // [kF][2] per-warp halves of a frame's energy sum
+  float* fbw_s = red_s + kF * 2;                                    // [n_w]
   int* meta_s = reinterpret_cast<int*>(fbw_s + ((p.n_w + 3) & ~3)); // [3][n_mels]
 
   const int tid = threadIdx.x;
@@ -305,9 +304,8 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
     e = fmaf(1024.f, e + eo, x0sq + xnsq);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-    if ((t & 31) == 0) red_s[g * 2 + (t >> 5)] = e;
-    group_sync(g);   // (also: every thread has read its pass-2 values before the next frame's pass 1 overwrites them)
-    if (t == 0) energy_s[fl] = sqrtf(0.5f * (red_s[g * 2] + red_s[g * 2 + 1]) + 513e-9f);
+    if ((t & 31) == 0) red_s[fl * 2 + (t >> 5)] = e;   // the two warps' halves of the frame: combined after the loop
+    group_sync(g);   // every thread has read its pass-3 values before the next frame's pass 1 overwrites the buffer
   }
   __syncthreads();
 
@@ -337,7 +335,9 @@ __global__ void __launch_bounds__(kThreads, 2) mel_kernel(const MelParams p) {
       // [0.5, 2], 2^-21.4 inside), against the 1e-5 L1 bound of the parity tests; logf costs ~10x the instructions
       if (lane < nf) p.mel[((long long)b * p.n_mels + m) * p.T + f0 + lane] = __logf(fmaxf(acc, 1e-5f));
     }
-    if (p.energy && tid < nf) p.energy[(long long)b * p.T + f0 + tid] = energy_s[tid];
+    // (one thread per frame here instead of a divergent tail behind every frame's last barrier)
+    if (p.energy && tid < nf)
+      p.energy[(long long)b * p.T + f0 + tid] = sqrtf(0.5f * (red_s[2 * tid] + red_s[2 * tid + 1]) + 513e-9f);
   }
 }
 
@@ -395,7 +395,7 @@ extern "C" int e2e_mel_create(int32_t n_fft, int32_t hop_length, int32_t win_len
     tw[n] = make_float2((float)cos(2.0 * pi * n / kNfft), (float)(-sin(2.0 * pi * n / kNfft)));
   }
   // mirrors the carve-up at the top of mel_kernel
-  m->smem_bytes = (kAudio + 2 * kGroups * kSx + kF * m->magp + kF + kGroups * 2 + ((m->n_w + 3) & ~3) + 3 * n_mels) * 4;
+  m->smem_bytes = (kAudio + 2 * kGroups * kSx + kF * m->magp + kF * 2 + ((m->n_w + 3) & ~3) + 3 * n_mels) * 4;
   if (m->smem_bytes > 227 * 1024) {
     delete m;
     return fail(-4, "mel filterbank too dense for the shared-memory budget");
