@@ -446,8 +446,8 @@ def side_workloads(voc, dev, peaks, quick: bool):
                                   "algorithmic_bytes": alg, "hbm_floor_ms": alg / (peaks["hbm"] * 1e9) * 1e3,
                                   "issue_slot_floor_ms": issue_floor_ms, "issue_slot_frac": issue_floor_ms / ms,
                                   "note": "SURVEY.md §8 d7 names HBM as this path's roofline and `frac` is reported against it; "
-                                          "the kernel is bound by dependent-instruction latency at ~50 % issue-slot use (%d warp instructions "
-                                          "per frame, ncu): " % MEL_WARP_INSTR_PER_FRAME +
+                                          "the kernel is bound by dependent-instruction latency at about half of the issue slots "
+                                          "(%d warp instructions per frame, ncu): " % MEL_WARP_INSTR_PER_FRAME +
                                           "issue_slot_frac = time at 100 % issue-slot use / measured time",
                                   "peak_source": peaks["source"]}}
     del wav, mel, en
